@@ -1,0 +1,107 @@
+/*
+ * tcgnn_b200 -- C ABI of the B200-native TC-GNN aggregation path (SGT + SpMM + SDDMM).
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch types.
+ * The Python extension module `TCGNN` (tc-gnn_atc23_b200/csrc/binding.cpp) is a thin
+ * torch-aware caller of exactly these entry points; INTEGRATION.md shows how the reference's
+ * own TCGNN.cpp would bind them.  All functions return 0 on success or a negative
+ * tcgnn_status; they never call exit(), never synchronise the device unless stated, and
+ * launch on the stream they are given (`stream` is a cudaStream_t passed as void*).
+ *
+ * Reference interfaces replaced (paths relative to the reference repo):
+ *   tcgnn_sgt_cpu      <- preprocess            TCGNN_conv/TCGNN.cpp:172-226
+ *   tcgnn_sgt_cuda     <- preprocess_gpu        TCGNN_conv/TCGNN.cpp:229-256 (+ fill_edgeToRow /
+ *                         fill_window stubs     TCGNN_conv/TCGNN_kernel.cu:21-119)
+ *   tcgnn_spmm_f32     <- spmm_forward_cuda     TCGNN_conv/TCGNN_kernel.cu:175-220 (kernel :336-454)
+ *                         spmmAGNN_forward_cuda TCGNN_conv/TCGNN_kernel.cu:227-279 (kernel :459-578)
+ *   tcgnn_sddmm_f32    <- sddmm_forward_cuda    TCGNN_conv/TCGNN_kernel.cu:286-327 (kernel :584-728)
+ *   tcgnn_plan_*       <- (new) the kernel-side layout derived once per graph from the SGT arrays;
+ *                         the reference re-derives it inside every kernel launch by rescanning all
+ *                         window edges per tile (TCGNN_kernel.cu:399-408).
+ */
+#ifndef TCGNN_B200_H
+#define TCGNN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TCGNN_BLK_H 16 /* TCGNN_conv/config.h:4 */
+#define TCGNN_BLK_W 8  /* TCGNN_conv/config.h:5 */
+
+typedef enum tcgnn_status {
+  TCGNN_OK = 0,
+  TCGNN_ERR_INVALID_ARG = -1, /* null pointer, negative size, unsupported blk_h / blk_w, bad alignment */
+  TCGNN_ERR_CUDA = -2,        /* a CUDA runtime call or a kernel launch failed (see tcgnn_last_error) */
+  TCGNN_ERR_NO_DEVICE = -3,   /* no CUDA device / not an sm_100 device */
+  TCGNN_ERR_OOM = -4,         /* host or device allocation failed */
+  TCGNN_ERR_OVERFLOW = -5     /* tile or edge count does not fit the 32-bit plan indices */
+} tcgnn_status;
+
+typedef struct tcgnn_plan tcgnn_plan; /* opaque, owns device memory */
+
+/* Library / diagnostics ------------------------------------------------------------------- */
+int tcgnn_version(void);                    /* 10000*major + 100*minor + patch */
+const char* tcgnn_status_string(int status);
+const char* tcgnn_last_error(void);         /* thread-local detail of the last failure */
+
+/* SGT (sparse-graph translation) ------------------------------------------------------------
+ * Bit-exact with the reference `preprocess` (TCGNN.cpp:172-226):
+ *   edge_to_row[e]      = row owning edge e
+ *   S_w                 = sorted unique col_idx over the edges of window w (blk_h rows)
+ *   edge_to_col[e]      = rank of col_idx[e] in S_w
+ *   block_partition[w]  = ceil(max(|S_w|, 1) / blk_w)        (empty window -> 1, as the reference)
+ * *tc_blocks_out (nullable) receives sum(block_partition) (+1 when num_nodes % blk_h == 0, the
+ * total the reference prints at TCGNN.cpp:225; its out-of-bounds write is not reproduced).
+ * Host version: all pointers are host memory; num_threads <= 0 means all hardware threads.
+ * Device version: all pointers are device memory; *tc_blocks_out is host memory and, when
+ * non-null, the call synchronises `stream` to fill it. */
+int tcgnn_sgt_cpu(const int32_t* row_ptr, const int32_t* col_idx, int32_t num_nodes, int64_t num_edges,
+                  int32_t blk_h, int32_t blk_w, int32_t* block_partition, int32_t* edge_to_col,
+                  int32_t* edge_to_row, int64_t* tc_blocks_out, int32_t num_threads);
+int tcgnn_sgt_cuda(const int32_t* row_ptr, const int32_t* col_idx, int32_t num_nodes, int64_t num_edges,
+                   int32_t blk_h, int32_t blk_w, int32_t* block_partition, int32_t* edge_to_col,
+                   int32_t* edge_to_row, int64_t* tc_blocks_out, void* stream);
+
+/* Plan ---------------------------------------------------------------------------------------
+ * Derives the kernel-side tile stream from the caller's SGT arrays (all device pointers, the
+ * same five arrays the reference kernels take, TCGNN_kernel.cu:336-346).  One 64-byte record
+ * per 16x8 TC block: the 8 gathered feature rows, a 128-bit occupancy mask, the owning window
+ * and the offset of its edges in tile order.  Synchronises `stream` (it needs the tile total). */
+int tcgnn_plan_create(const int32_t* row_ptr, const int32_t* col_idx, const int32_t* block_partition,
+                      const int32_t* edge_to_col, const int32_t* edge_to_row, int32_t num_nodes,
+                      int64_t num_edges, int32_t num_windows, void* stream, tcgnn_plan** plan_out);
+int tcgnn_plan_destroy(tcgnn_plan* plan);
+/* info[0]=num_nodes info[1]=num_edges info[2]=num_windows info[3]=num_tiles info[4]=plan bytes
+ * info[5]=distinct (row,col) pairs info[6]=device ordinal info[7]=SM count */
+int tcgnn_plan_info(const tcgnn_plan* plan, int64_t info[8]);
+
+/* SpMM: Y[i,:] = sum_{e in row i} w_e * tf32(X[col_idx[e],:])      (fp32 accumulate)
+ * edge_weight == NULL  -> w_e = 1 (pattern; GCN/GIN/SAG aggregation, TCGNN_kernel.cu:336-454)
+ * edge_weight != NULL  -> w_e = tf32(edge_weight[e]), CSR edge order (AGNN, :459-578)
+ * X: [num_nodes, dim] row-major with leading dimension ldx (floats); Y likewise with ldy; Y is
+ * fully overwritten (rows of empty windows become 0).  Any dim >= 1 (the reference drops
+ * dim % 16 tails and columns >= 128). */
+int tcgnn_spmm_f32(tcgnn_plan* plan, const float* x, int64_t ldx, const float* edge_weight,
+                   float* y, int64_t ldy, int32_t dim, void* stream);
+
+/* SDDMM: edge_out[e] = sum_k tf32(X[row(e),k]) * tf32(X[col_idx[e],k])   (TCGNN_kernel.cu:584-728)
+ * edge_out: [num_edges] fp32, CSR edge order, fully overwritten. */
+int tcgnn_sddmm_f32(tcgnn_plan* plan, const float* x, int64_t ldx, float* edge_out, int32_t dim,
+                    void* stream);
+
+/* Bring-up self test: runs single tcgen05 MMAs with known operands through the exact shared
+ * memory layouts / descriptors the kernels use and compares with a scalar computation.
+ * Returns 0 when every probe matches; max_abs_err[i] (nullable, 8 floats) gets per-probe errors. */
+int tcgnn_selftest_umma(float* max_abs_err, void* stream);
+
+/* Number of kernels launched by the calling thread through this library since the last reset
+ * (bench.py's gpu_launches). */
+int64_t tcgnn_launch_count(int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TCGNN_B200_H */

@@ -1,0 +1,205 @@
+// Shared device helpers for the sm_100a kernels: PTX wrappers for mbarrier, TMA bulk copies,
+// tcgen05 (UMMA / TMEM), proxy fences, and the TF32 rounding the reference applies
+// (wmma::__float_to_tf32 == cvt.rna.tf32.f32, /root/reference TCGNN_kernel.cu:436-444).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/tcgnn_b200.h"
+
+namespace tcgnn {
+
+// ---------------------------------------------------------------------------------------------
+// Plan layout shared by plan.cu / spmm_tc.cu / sddmm_tc.cu
+// ---------------------------------------------------------------------------------------------
+struct __align__(16) TileMeta {  // one 16x8 TC block of the reference's SGT, 64 bytes
+  int32_t cols[8];     // X row gathered for condensed column c (-1: padding, contributes zeros)
+  uint32_t mask[4];    // bit (r*8+c): word r/4, bit (r%4)*8+c  <=> edge (window row r, condensed col c)
+  int32_t win;         // owning row window
+  int32_t edge_ofs;    // offset of the tile's first edge in tile order (exclusive scan of popcounts)
+  uint32_t flags;      // bit0: first tile of its window, bit1: last tile of its window
+  int32_t reserved;
+};
+static_assert(sizeof(TileMeta) == 64, "TileMeta must be 64 bytes");
+
+constexpr uint32_t kTileFirst = 1u;
+constexpr uint32_t kTileLast = 2u;
+
+struct PlanView {  // device pointers, passed by value to kernels
+  const TileMeta* tiles;        // [num_tiles]
+  const int32_t* win_tile_ptr;  // [num_windows + 1] exclusive scan of blockPartition
+  const int32_t* eperm;         // [num_pairs] tile order -> CSR edge id (lazy; weighted SpMM / SDDMM)
+  int32_t num_nodes;
+  int32_t num_windows;
+  int32_t num_tiles;
+  int32_t num_pairs;
+};
+
+// ---------------------------------------------------------------------------------------------
+// small utilities
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+// cvt.rna.tf32.f32: round to nearest, ties away from zero, 10 mantissa bits (crt/mma.h:96-103).
+__device__ __forceinline__ float tf32_rna(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+__device__ __forceinline__ float4 tf32_rna4(float4 v) {
+  return make_float4(tf32_rna(v.x), tf32_rna(v.y), tf32_rna(v.z), tf32_rna(v.w));
+}
+
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// mbarrier
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Wait with a watchdog: a protocol bug must surface as a launch failure, never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if ((++spins & 0x3FFu) == 0 && clock64() - t0 > 4000000000LL) {  // ~2 s at 1.9 GHz
+      asm volatile("trap;");
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// proxy fences / TMA 1-D bulk copy (SASS: UBLKCP)
+// ---------------------------------------------------------------------------------------------
+// generic-proxy smem writes -> visible to the async proxy (tcgen05.mma operand reads)
+__device__ __forceinline__ void fence_proxy_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes,
+                                             uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
+// tcgen05: TMEM allocation, MMA, commit, TMEM loads
+// ---------------------------------------------------------------------------------------------
+template <uint32_t kCols>
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_result) {  // whole warp, .sync.aligned
+  static_assert(kCols >= 32 && kCols <= 512 && (kCols & (kCols - 1)) == 0, "TMEM columns: pow2 in [32,512]");
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)),
+               "n"(kCols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <uint32_t kCols>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {  // whole warp
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kCols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc], tf32 inputs, fp32 accumulate.  One thread issues.
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// mbarrier arrives once all previously issued MMAs of this thread have completed
+// (implies tcgen05.fence::before_thread_sync).
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+// 32 lanes x 16 consecutive fp32 columns: thread t of the warp reads TMEM lane (warp%4)*32+t.
+__device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ---------------------------------------------------------------------------------------------
+// UMMA descriptors (bit layout: PTX ISA "tcgen05 matrix descriptor" / "instruction descriptor")
+// ---------------------------------------------------------------------------------------------
+// Shared-memory matrix descriptor: start address, leading/stride byte offsets (all >>4),
+// descriptor version 1 (Blackwell) at bits [46,48), swizzle mode at bits [61,64).
+constexpr uint64_t kSwizzleNone = 0, kSwizzle128B = 2;
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                                   uint64_t swizzle) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);        // [0,14)
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;   // [16,30)
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;   // [32,46)
+  d |= 1ull << 46;                                                // version = 1
+  d |= swizzle << 61;                                             // layout type
+  return d;
+}
+// Instruction descriptor for kind::tf32, fp32 accumulate.
+//   [4,6) D format = 1 (f32)   [7,10) A format = 2 (tf32)   [10,13) B format = 2 (tf32)
+//   bit 15 A major (1 = MN-major)   bit 16 B major (1 = MN-major)
+//   [17,23) N >> 3              [24,29) M >> 4
+__host__ __device__ constexpr uint32_t make_idesc_tf32(uint32_t m, uint32_t n, bool a_mn_major, bool b_mn_major) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(a_mn_major) << 15) |
+         (static_cast<uint32_t>(b_mn_major) << 16) | ((n >> 3) << 17) | ((m >> 4) << 24);
+}
+
+// Byte offset of the 16-byte chunk `chunk16` (0..7) of 128-byte row `row` inside a 1024-byte
+// 128B-swizzle atom whose base is 1024-byte aligned (chunk index XOR row, Swizzle<3,4,3>).
+__device__ __forceinline__ uint32_t sw128_offset(uint32_t row, uint32_t chunk16) {
+  return row * 128u + ((chunk16 ^ (row & 7u)) << 4);
+}
+
+}  // namespace tcgnn
