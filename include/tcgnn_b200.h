@@ -92,10 +92,14 @@ int tcgnn_spmm_f32(tcgnn_plan* plan, const float* x, int64_t ldx, const float* e
 int tcgnn_sddmm_f32(tcgnn_plan* plan, const float* x, int64_t ldx, float* edge_out, int32_t dim,
                     void* stream);
 
-/* Bring-up self test: runs single tcgen05 MMAs with known operands through the exact shared
- * memory layouts / descriptors the kernels use and compares with a scalar computation.
- * Returns 0 when every probe matches; max_abs_err[i] (nullable, 8 floats) gets per-probe errors. */
-int tcgnn_selftest_umma(float* max_abs_err, void* stream);
+/* Bring-up / layout diagnostics (used by tests/test_gpu_umma_layouts.py): copies the two byte images
+ * into 1024-byte aligned shared memory, issues `ksteps` tcgen05.mma.kind::tf32 (M=128) whose
+ * descriptors are adesc/bdesc (start-address field 0) plus the image base plus k*a_step_bytes /
+ * k*b_step_bytes, and returns the 128 x ncols fp32 accumulator (row = TMEM lane) in d_out (HOST
+ * memory).  ncols must be 16, 32 or 64 and equal the N of idesc.  Synchronises the stream. */
+int tcgnn_debug_umma(const void* a_image, int32_t a_bytes, const void* b_image, int32_t b_bytes,
+                     uint64_t adesc, uint64_t bdesc, uint32_t idesc, int32_t ksteps, int32_t a_step_bytes,
+                     int32_t b_step_bytes, float* d_out, int32_t ncols, void* stream);
 
 /* Number of kernels launched by the calling thread through this library since the last reset
  * (bench.py's gpu_launches). */

@@ -1,0 +1,151 @@
+// extern "C" surface of include/tcgnn_b200.h: argument validation, error strings, launch counter.
+#include <stdarg.h>
+#include <stdio.h>
+
+#include "plan.h"
+
+namespace tcgnn {
+
+static thread_local char g_last_error[512] = "";
+static thread_local int64_t g_launches = 0;
+
+void set_last_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_last_error, sizeof(g_last_error), fmt, ap);
+  va_end(ap);
+}
+void count_launch(int n) { g_launches += n; }
+
+int sgt_cpu(const int32_t* row_ptr, const int32_t* col_idx, int32_t num_nodes, int64_t num_edges, int32_t blk_h,
+            int32_t blk_w, int32_t* block_partition, int32_t* edge_to_col, int32_t* edge_to_row,
+            int64_t* tc_blocks_out, int32_t num_threads);
+
+}  // namespace tcgnn
+
+using namespace tcgnn;
+
+extern "C" {
+
+int tcgnn_version(void) { return 100; /* 0.1.0 */ }
+
+const char* tcgnn_status_string(int status) {
+  switch (status) {
+    case TCGNN_OK: return "ok";
+    case TCGNN_ERR_INVALID_ARG: return "invalid argument";
+    case TCGNN_ERR_CUDA: return "CUDA error";
+    case TCGNN_ERR_NO_DEVICE: return "no sm_100 CUDA device";
+    case TCGNN_ERR_OOM: return "out of memory";
+    case TCGNN_ERR_OVERFLOW: return "32-bit index overflow";
+    default: return "unknown status";
+  }
+}
+
+const char* tcgnn_last_error(void) { return g_last_error; }
+
+int64_t tcgnn_launch_count(int reset) {
+  const int64_t v = g_launches;
+  if (reset) g_launches = 0;
+  return v;
+}
+
+int tcgnn_sgt_cpu(const int32_t* row_ptr, const int32_t* col_idx, int32_t num_nodes, int64_t num_edges,
+                  int32_t blk_h, int32_t blk_w, int32_t* block_partition, int32_t* edge_to_col,
+                  int32_t* edge_to_row, int64_t* tc_blocks_out, int32_t num_threads) {
+  return sgt_cpu(row_ptr, col_idx, num_nodes, num_edges, blk_h, blk_w, block_partition, edge_to_col, edge_to_row,
+                 tc_blocks_out, num_threads);
+}
+
+int tcgnn_sgt_cuda(const int32_t* row_ptr, const int32_t* col_idx, int32_t num_nodes, int64_t num_edges,
+                   int32_t blk_h, int32_t blk_w, int32_t* block_partition, int32_t* edge_to_col,
+                   int32_t* edge_to_row, int64_t* tc_blocks_out, void* stream) {
+  if (row_ptr == nullptr || block_partition == nullptr || num_nodes < 0 || num_edges < 0 || blk_h <= 0 ||
+      blk_w <= 0 || (num_edges > 0 && (col_idx == nullptr || edge_to_col == nullptr || edge_to_row == nullptr))) {
+    set_last_error("tcgnn_sgt_cuda: bad argument");
+    return TCGNN_ERR_INVALID_ARG;
+  }
+  return sgt_cuda(row_ptr, col_idx, num_nodes, num_edges, blk_h, blk_w, block_partition, edge_to_col, edge_to_row,
+                  tc_blocks_out, static_cast<cudaStream_t>(stream));
+}
+
+int tcgnn_plan_create(const int32_t* row_ptr, const int32_t* col_idx, const int32_t* block_partition,
+                      const int32_t* edge_to_col, const int32_t* edge_to_row, int32_t num_nodes, int64_t num_edges,
+                      int32_t num_windows, void* stream, tcgnn_plan** plan_out) {
+  if (plan_out == nullptr) {
+    set_last_error("tcgnn_plan_create: plan_out is null");
+    return TCGNN_ERR_INVALID_ARG;
+  }
+  *plan_out = nullptr;
+  const int64_t expect_windows = (static_cast<int64_t>(num_nodes) + TCGNN_BLK_H - 1) / TCGNN_BLK_H;
+  if (row_ptr == nullptr || block_partition == nullptr || num_nodes <= 0 || num_edges < 0 ||
+      num_edges > 0x7FFFFFFFLL || num_windows != expect_windows ||
+      (num_edges > 0 && (col_idx == nullptr || edge_to_col == nullptr || edge_to_row == nullptr))) {
+    set_last_error("tcgnn_plan_create: bad argument (num_nodes=%d num_edges=%lld num_windows=%d, expected %lld "
+                   "windows of %d rows)",
+                   num_nodes, static_cast<long long>(num_edges), num_windows, static_cast<long long>(expect_windows),
+                   TCGNN_BLK_H);
+    return TCGNN_ERR_INVALID_ARG;
+  }
+  return plan_create(row_ptr, col_idx, block_partition, edge_to_col, edge_to_row, num_nodes, num_edges, num_windows,
+                     static_cast<cudaStream_t>(stream), plan_out);
+}
+
+int tcgnn_plan_destroy(tcgnn_plan* plan) { return plan_destroy(plan); }
+
+int tcgnn_plan_info(const tcgnn_plan* plan, int64_t info[8]) {
+  if (plan == nullptr || info == nullptr) return TCGNN_ERR_INVALID_ARG;
+  info[0] = plan->num_nodes;
+  info[1] = plan->num_edges;
+  info[2] = plan->num_windows;
+  info[3] = plan->num_tiles;
+  info[4] = static_cast<int64_t>(sizeof(TileMeta)) * (plan->num_tiles + 1) +
+            4 * (static_cast<int64_t>(plan->num_windows) + 1) + (plan->eperm ? 4LL * plan->num_pairs : 0) +
+            (plan->weight_perm ? 4LL * plan->num_pairs : 0) + (plan->sddmm_perm ? 4LL * plan->num_pairs : 0) +
+            (plan->groups ? 16LL * plan->num_groups : 0);
+  info[5] = plan->num_pairs;
+  info[6] = plan->device;
+  info[7] = plan->num_sms;
+  return TCGNN_OK;
+}
+
+static int check_op(const char* what, const tcgnn_plan* plan, const float* x, int64_t ldx, const void* out,
+                    int32_t dim) {
+  if (plan == nullptr || x == nullptr || out == nullptr || dim < 1 || ldx < dim) {
+    set_last_error("%s: bad argument (plan=%p x=%p out=%p dim=%d ldx=%lld)", what, (const void*)plan,
+                   (const void*)x, out, dim, static_cast<long long>(ldx));
+    return TCGNN_ERR_INVALID_ARG;
+  }
+  int dev = -1;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev != plan->device) {
+    set_last_error("%s: current device %d differs from the plan's device %d", what, dev, plan->device);
+    return TCGNN_ERR_INVALID_ARG;
+  }
+  return TCGNN_OK;
+}
+
+int tcgnn_spmm_f32(tcgnn_plan* plan, const float* x, int64_t ldx, const float* edge_weight, float* y, int64_t ldy,
+                   int32_t dim, void* stream) {
+  int st = check_op("tcgnn_spmm_f32", plan, x, ldx, y, dim);
+  if (st != TCGNN_OK) return st;
+  if (ldy < dim) {
+    set_last_error("tcgnn_spmm_f32: ldy < dim");
+    return TCGNN_ERR_INVALID_ARG;
+  }
+  return spmm_launch(plan, x, ldx, edge_weight, y, ldy, dim, static_cast<cudaStream_t>(stream));
+}
+
+int tcgnn_sddmm_f32(tcgnn_plan* plan, const float* x, int64_t ldx, float* edge_out, int32_t dim, void* stream) {
+  if (plan != nullptr && plan->num_edges == 0) return TCGNN_OK;
+  int st = check_op("tcgnn_sddmm_f32", plan, x, ldx, edge_out, dim);
+  if (st != TCGNN_OK) return st;
+  return sddmm_launch(plan, x, ldx, edge_out, dim, static_cast<cudaStream_t>(stream));
+}
+
+int tcgnn_debug_umma(const void* a_image, int32_t a_bytes, const void* b_image, int32_t b_bytes, uint64_t adesc,
+                     uint64_t bdesc, uint32_t idesc, int32_t ksteps, int32_t a_step_bytes, int32_t b_step_bytes,
+                     float* d_out, int32_t ncols, void* stream) {
+  return debug_umma(a_image, a_bytes, b_image, b_bytes, adesc, bdesc, idesc, ksteps, a_step_bytes, b_step_bytes,
+                    d_out, ncols, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,402 @@
+// Plan builder: turns the reference's SGT arrays (blockPartition / edgeToColumn / edgeToRow,
+// /root/reference TCGNN.cpp:172-226) into a tile stream the tcgen05 kernels can consume without
+// the per-tile rescan of all window edges the reference kernels do (TCGNN_kernel.cu:399-408).
+//
+// All work is on the device; the only host round trip is the tile total (needed to size the
+// allocation).  Integer-only, HBM-bound: plain coalesced kernels, grid-stride.
+#include <stdio.h>
+
+#include <new>
+
+#include "plan.h"
+
+namespace tcgnn {
+
+// ------------------------------------------------------------------------------------------
+// exclusive scan of int32 (three-pass: block sums -> scan of sums -> add back)
+// ------------------------------------------------------------------------------------------
+constexpr int kScanThreads = 256;
+constexpr int kScanItems = 16;
+constexpr int kScanTile = kScanThreads * kScanItems;
+
+template <typename Load>
+__device__ __forceinline__ void block_scan_tile(Load load, int64_t n, int64_t base, int32_t* out, int32_t carry_in,
+                                                int32_t* tile_total) {
+  __shared__ int32_t warp_sums[kScanThreads / 32];
+  const int tid = threadIdx.x;
+  int32_t vals[kScanItems];
+  int32_t thread_sum = 0;
+  const int64_t first = base + static_cast<int64_t>(tid) * kScanItems;
+#pragma unroll
+  for (int i = 0; i < kScanItems; ++i) {
+    const int64_t idx = first + i;
+    vals[i] = idx < n ? load(idx) : 0;
+    thread_sum += vals[i];
+  }
+  // warp inclusive scan of thread sums
+  int32_t incl = thread_sum;
+#pragma unroll
+  for (int ofs = 1; ofs < 32; ofs <<= 1) {
+    int32_t t = __shfl_up_sync(0xffffffffu, incl, ofs);
+    if ((tid & 31) >= ofs) incl += t;
+  }
+  if ((tid & 31) == 31) warp_sums[tid >> 5] = incl;
+  __syncthreads();
+  int32_t warp_prefix = 0;
+  int32_t total = 0;
+#pragma unroll
+  for (int w = 0; w < kScanThreads / 32; ++w) {
+    const int32_t s = warp_sums[w];
+    if (w < (tid >> 5)) warp_prefix += s;
+    total += s;
+  }
+  if (out != nullptr) {
+    int32_t run = carry_in + warp_prefix + incl - thread_sum;
+#pragma unroll
+    for (int i = 0; i < kScanItems; ++i) {
+      const int64_t idx = first + i;
+      if (idx < n) out[idx] = run;
+      run += vals[i];
+    }
+  }
+  if (tile_total != nullptr && tid == 0) *tile_total = total;
+  __syncthreads();
+}
+
+struct LoadClampedBp {  // max(blockPartition[w], 1): a window always owns at least one tile
+  const int32_t* bp;
+  __device__ int32_t operator()(int64_t i) const { return max(bp[i], 1); }
+};
+struct LoadWindowGroups {  // SDDMM work units per window: ceil(tiles / 16)
+  const int32_t* win_tile_ptr;
+  __device__ int32_t operator()(int64_t i) const { return (win_tile_ptr[i + 1] - win_tile_ptr[i] + 15) >> 4; }
+};
+struct LoadTilePopc {
+  const TileMeta* tiles;
+  __device__ int32_t operator()(int64_t i) const {
+    const uint4 m = *reinterpret_cast<const uint4*>(tiles[i].mask);
+    return __popc(m.x) + __popc(m.y) + __popc(m.z) + __popc(m.w);
+  }
+};
+
+template <typename Load>
+__global__ void __launch_bounds__(kScanThreads) scan_block_sums(Load load, int64_t n, int32_t* block_sums) {
+  block_scan_tile(load, n, static_cast<int64_t>(blockIdx.x) * kScanTile, nullptr, 0, &block_sums[blockIdx.x]);
+}
+// single block: exclusive scan of block sums in place; writes the grand total to sums[nblocks]
+__global__ void __launch_bounds__(kScanThreads) scan_sums_inplace(int32_t* sums, int32_t nblocks) {
+  __shared__ int32_t carry;
+  __shared__ int32_t tile_total;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  struct L {
+    const int32_t* p;
+    __device__ int32_t operator()(int64_t i) const { return p[i]; }
+  } load{sums};
+  for (int64_t base = 0; base < nblocks; base += kScanTile) {
+    const int32_t c = carry;
+    block_scan_tile(load, nblocks, base, sums, c, &tile_total);
+    if (threadIdx.x == 0) carry = c + tile_total;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) sums[nblocks] = carry;
+}
+template <typename Load>
+__global__ void __launch_bounds__(kScanThreads) scan_apply(Load load, int64_t n, const int32_t* block_offsets,
+                                                          int32_t* out) {
+  block_scan_tile(load, n, static_cast<int64_t>(blockIdx.x) * kScanTile, out, block_offsets[blockIdx.x], nullptr);
+}
+
+// out[0..n) = exclusive scan, out[n] = total (also left in scratch[nblocks]).
+template <typename Load>
+static cudaError_t exclusive_scan(Load load, int64_t n, int32_t* out, int32_t* scratch, cudaStream_t stream) {
+  const int nblocks = static_cast<int>((n + kScanTile - 1) / kScanTile);
+  if (nblocks > 0) {
+    scan_block_sums<<<nblocks, kScanThreads, 0, stream>>>(load, n, scratch);
+    count_launch();
+  }
+  scan_sums_inplace<<<1, kScanThreads, 0, stream>>>(scratch, nblocks);
+  count_launch();
+  if (nblocks > 0) {
+    scan_apply<<<nblocks, kScanThreads, 0, stream>>>(load, n, scratch, out);
+    count_launch();
+  }
+  return cudaMemcpyAsync(out + n, scratch + nblocks, sizeof(int32_t), cudaMemcpyDeviceToDevice, stream);
+}
+
+// ------------------------------------------------------------------------------------------
+// tile records
+// ------------------------------------------------------------------------------------------
+__global__ void init_tiles_kernel(TileMeta* tiles, const int32_t* __restrict__ win_tile_ptr, int32_t num_windows,
+                                  int32_t num_tiles) {
+  for (int64_t g = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; g < num_tiles;
+       g += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    // window = last w with win_tile_ptr[w] <= g
+    int32_t lo = 0, hi = num_windows;
+    while (hi - lo > 1) {
+      const int32_t mid = (lo + hi) >> 1;
+      if (win_tile_ptr[mid] <= g) lo = mid; else hi = mid;
+    }
+    uint32_t flags = 0;
+    if (win_tile_ptr[lo] == g) flags |= kTileFirst;
+    if (win_tile_ptr[lo + 1] == g + 1) flags |= kTileLast;
+    uint4* rec = reinterpret_cast<uint4*>(tiles + g);
+    rec[0] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);  // cols[0..3] = -1
+    rec[1] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);  // cols[4..7] = -1
+    rec[2] = make_uint4(0, 0, 0, 0);                                          // mask
+    rec[3] = make_uint4(static_cast<uint32_t>(lo), 0u, flags, 0u);            // win, edge_ofs, flags, reserved
+  }
+}
+
+// One thread per CSR edge: record the gathered row and set the occupancy bit of its tile.
+// Edges whose SGT entries are inconsistent (column rank outside the window's tiles, row outside
+// the graph) are counted in *bad and skipped instead of corrupting memory.
+__global__ void scatter_edges_kernel(TileMeta* tiles, const int32_t* __restrict__ win_tile_ptr,
+                                     const int32_t* __restrict__ col_idx, const int32_t* __restrict__ edge_to_col,
+                                     const int32_t* __restrict__ edge_to_row, int64_t num_edges, int32_t num_nodes,
+                                     int32_t* bad) {
+  for (int64_t e = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; e < num_edges;
+       e += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int32_t r = edge_to_row[e];
+    const int32_t c = edge_to_col[e];
+    const int32_t x = col_idx[e];
+    if (r < 0 || r >= num_nodes || c < 0 || x < 0 || x >= num_nodes) { atomicAdd(bad, 1); continue; }
+    const int32_t w = r / TCGNN_BLK_H;
+    const int32_t t0 = win_tile_ptr[w];
+    const int32_t g = t0 + c / TCGNN_BLK_W;
+    if (g >= win_tile_ptr[w + 1]) { atomicAdd(bad, 1); continue; }
+    const int32_t rl = r % TCGNN_BLK_H, cl = c % TCGNN_BLK_W;
+    tiles[g].cols[cl] = x;  // every edge of this (window, rank) carries the same column id
+    atomicOr(&tiles[g].mask[rl >> 2], 1u << ((rl & 3) * 8 + cl));
+  }
+}
+
+__global__ void store_edge_ofs_kernel(TileMeta* tiles, const int32_t* __restrict__ tile_ofs, int32_t num_tiles) {
+  for (int64_t g = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; g < num_tiles;
+       g += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    tiles[g].edge_ofs = tile_ofs[g];
+}
+
+__global__ void eperm_kernel(const TileMeta* __restrict__ tiles, const int32_t* __restrict__ win_tile_ptr,
+                             const int32_t* __restrict__ edge_to_col, const int32_t* __restrict__ edge_to_row,
+                             int64_t num_edges, int32_t* eperm) {
+  for (int64_t e = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; e < num_edges;
+       e += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int32_t r = edge_to_row[e];
+    const int32_t c = edge_to_col[e];
+    const int32_t w = r / TCGNN_BLK_H;
+    const int32_t g = win_tile_ptr[w] + c / TCGNN_BLK_W;
+    const int32_t rl = r % TCGNN_BLK_H, cl = c % TCGNN_BLK_W;
+    const TileMeta& t = tiles[g];
+    const int word = rl >> 2, bit = (rl & 3) * 8 + cl;
+    int rank = __popc(t.mask[word] & ((1u << bit) - 1u));
+    for (int i = 0; i < word; ++i) rank += __popc(t.mask[i]);
+    eperm[t.edge_ofs + rank] = static_cast<int32_t>(e);  // duplicated (row, col): one edge wins, as in the reference
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+static int grid_for(int64_t n, int threads) {
+  int64_t g = (n + threads - 1) / threads;
+  if (g < 1) g = 1;
+  if (g > 148 * 32) g = 148 * 32;
+  return static_cast<int>(g);
+}
+
+#define PLAN_CUDA(expr)                                                                   \
+  do {                                                                                    \
+    cudaError_t _e = (expr);                                                              \
+    if (_e != cudaSuccess) {                                                              \
+      set_last_error("%s failed: %s", #expr, cudaGetErrorString(_e));                     \
+      status = (_e == cudaErrorMemoryAllocation) ? TCGNN_ERR_OOM : TCGNN_ERR_CUDA;        \
+      goto fail;                                                                          \
+    }                                                                                     \
+  } while (0)
+
+int plan_create(const int32_t* row_ptr, const int32_t* col_idx, const int32_t* block_partition,
+                const int32_t* edge_to_col, const int32_t* edge_to_row, int32_t num_nodes, int64_t num_edges,
+                int32_t num_windows, cudaStream_t stream, tcgnn_plan** plan_out) {
+  int status = TCGNN_OK;
+  tcgnn_plan* p = new (std::nothrow) tcgnn_plan();
+  if (p == nullptr) return TCGNN_ERR_OOM;
+  int32_t* scratch = nullptr;
+  int32_t* tile_ofs = nullptr;
+  int32_t host_vals[2] = {0, 0};
+  int dev = 0;
+  p->row_ptr = row_ptr;
+  p->col_idx = col_idx;
+  p->edge_to_col = edge_to_col;
+  p->edge_to_row = edge_to_row;
+  p->num_nodes = num_nodes;
+  p->num_edges = num_edges;
+  p->num_windows = num_windows;
+  PLAN_CUDA(cudaGetDevice(&dev));
+  p->device = dev;
+  PLAN_CUDA(cudaDeviceGetAttribute(&p->num_sms, cudaDevAttrMultiProcessorCount, dev));
+  {
+    int major = 0;
+    PLAN_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+    if (major != 10) {
+      set_last_error("device %d has compute capability %d.x; this library is built for sm_100a only", dev, major);
+      status = TCGNN_ERR_NO_DEVICE;
+      goto fail;
+    }
+  }
+  {
+    const int64_t nblk_w = (static_cast<int64_t>(num_windows) + kScanTile - 1) / kScanTile;
+    PLAN_CUDA(cudaMalloc(&p->win_tile_ptr, sizeof(int32_t) * (static_cast<size_t>(num_windows) + 1)));
+    PLAN_CUDA(cudaMalloc(&scratch, sizeof(int32_t) * (static_cast<size_t>(nblk_w) + 2)));
+    PLAN_CUDA(exclusive_scan(LoadClampedBp{block_partition}, num_windows, p->win_tile_ptr, scratch, stream));
+    PLAN_CUDA(cudaMemcpyAsync(&host_vals[0], p->win_tile_ptr + num_windows, sizeof(int32_t), cudaMemcpyDeviceToHost,
+                              stream));
+    PLAN_CUDA(cudaStreamSynchronize(stream));
+    PLAN_CUDA(cudaFree(scratch));
+    scratch = nullptr;
+  }
+  if (host_vals[0] < 0) {
+    set_last_error("tile count overflows int32");
+    status = TCGNN_ERR_OVERFLOW;
+    goto fail;
+  }
+  p->num_tiles = host_vals[0];
+  {
+    const size_t nt = static_cast<size_t>(p->num_tiles);
+    const int64_t nblk_t = (static_cast<int64_t>(nt) + kScanTile - 1) / kScanTile;
+    PLAN_CUDA(cudaMalloc(&p->tiles, sizeof(TileMeta) * (nt + 1)));
+    PLAN_CUDA(cudaMalloc(&scratch, sizeof(int32_t) * (static_cast<size_t>(nblk_t) + 2)));
+    PLAN_CUDA(cudaMalloc(&tile_ofs, sizeof(int32_t) * (nt + 1)));
+    PLAN_CUDA(cudaMalloc(&p->flag, sizeof(int32_t)));
+    PLAN_CUDA(cudaMemsetAsync(p->flag, 0, sizeof(int32_t), stream));
+    init_tiles_kernel<<<grid_for(p->num_tiles, 256), 256, 0, stream>>>(p->tiles, p->win_tile_ptr, num_windows,
+                                                                       p->num_tiles);
+    count_launch();
+    if (num_edges > 0) {
+      scatter_edges_kernel<<<grid_for(num_edges, 256), 256, 0, stream>>>(p->tiles, p->win_tile_ptr, col_idx,
+                                                                        edge_to_col, edge_to_row, num_edges,
+                                                                        num_nodes, p->flag);
+      count_launch();
+    }
+    PLAN_CUDA(exclusive_scan(LoadTilePopc{p->tiles}, p->num_tiles, tile_ofs, scratch, stream));
+    store_edge_ofs_kernel<<<grid_for(p->num_tiles, 256), 256, 0, stream>>>(p->tiles, tile_ofs, p->num_tiles);
+    count_launch();
+    PLAN_CUDA(cudaMemcpyAsync(&host_vals[0], tile_ofs + nt, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+    PLAN_CUDA(cudaMemcpyAsync(&host_vals[1], p->flag, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+    PLAN_CUDA(cudaStreamSynchronize(stream));
+    PLAN_CUDA(cudaGetLastError());
+    p->num_pairs = host_vals[0];
+    if (host_vals[1] != 0) {
+      set_last_error("%d edges have SGT entries inconsistent with blockPartition / num_nodes "
+                     "(edgeToColumn, edgeToRow and blockPartition must come from the same preprocess call)",
+                     host_vals[1]);
+      status = TCGNN_ERR_INVALID_ARG;
+      goto fail;
+    }
+    PLAN_CUDA(cudaFree(scratch));
+    scratch = nullptr;
+    PLAN_CUDA(cudaFree(tile_ofs));
+    tile_ofs = nullptr;
+  }
+  *plan_out = p;
+  return TCGNN_OK;
+fail:
+  if (scratch) cudaFree(scratch);
+  if (tile_ofs) cudaFree(tile_ofs);
+  plan_destroy(p);
+  return status;
+}
+
+int plan_ensure_eperm(tcgnn_plan* p, cudaStream_t stream) {
+  std::lock_guard<std::mutex> lock(p->mu);
+  if (p->eperm != nullptr || p->num_edges == 0) return TCGNN_OK;
+  int32_t* buf = nullptr;
+  cudaError_t e = cudaMalloc(&buf, sizeof(int32_t) * static_cast<size_t>(p->num_pairs > 0 ? p->num_pairs : 1));
+  if (e != cudaSuccess) {
+    set_last_error("cudaMalloc(eperm) failed: %s", cudaGetErrorString(e));
+    return TCGNN_ERR_OOM;
+  }
+  eperm_kernel<<<grid_for(p->num_edges, 256), 256, 0, stream>>>(p->tiles, p->win_tile_ptr, p->edge_to_col,
+                                                               p->edge_to_row, p->num_edges, buf);
+  count_launch();
+  e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    cudaFree(buf);
+    set_last_error("eperm kernel launch failed: %s", cudaGetErrorString(e));
+    return TCGNN_ERR_CUDA;
+  }
+  p->eperm = buf;
+  return TCGNN_OK;
+}
+
+__global__ void fill_groups_kernel(const int32_t* __restrict__ win_tile_ptr, const int32_t* __restrict__ win_group_ptr,
+                                   int32_t num_windows, int4* groups) {
+  for (int64_t w = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; w < num_windows;
+       w += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int32_t t0 = win_tile_ptr[w], t1 = win_tile_ptr[w + 1];
+    int32_t gi = win_group_ptr[w];
+    for (int32_t t = t0; t < t1; t += 16, ++gi) groups[gi] = make_int4(t, min(16, t1 - t), static_cast<int32_t>(w), 0);
+  }
+}
+
+int plan_ensure_groups(tcgnn_plan* p, cudaStream_t stream) {
+  std::lock_guard<std::mutex> lock(p->mu);
+  if (p->groups != nullptr) return TCGNN_OK;
+  int32_t* win_group_ptr = nullptr;
+  int32_t* scratch = nullptr;
+  int4* groups = nullptr;
+  int32_t total = 0;
+  const int64_t nblk = (static_cast<int64_t>(p->num_windows) + kScanTile - 1) / kScanTile;
+  cudaError_t e = cudaMalloc(&win_group_ptr, sizeof(int32_t) * (static_cast<size_t>(p->num_windows) + 1));
+  if (e == cudaSuccess) e = cudaMalloc(&scratch, sizeof(int32_t) * (static_cast<size_t>(nblk) + 2));
+  if (e == cudaSuccess)
+    e = exclusive_scan(LoadWindowGroups{p->win_tile_ptr}, p->num_windows, win_group_ptr, scratch, stream);
+  if (e == cudaSuccess)
+    e = cudaMemcpyAsync(&total, win_group_ptr + p->num_windows, sizeof(int32_t), cudaMemcpyDeviceToHost, stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+  if (e == cudaSuccess) e = cudaMalloc(&groups, sizeof(int4) * (static_cast<size_t>(total) + 1));
+  if (e == cudaSuccess) {
+    fill_groups_kernel<<<grid_for(p->num_windows, 256), 256, 0, stream>>>(p->win_tile_ptr, win_group_ptr,
+                                                                         p->num_windows, groups);
+    count_launch();
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+  if (win_group_ptr) cudaFree(win_group_ptr);
+  if (scratch) cudaFree(scratch);
+  if (e != cudaSuccess) {
+    if (groups) cudaFree(groups);
+    set_last_error("building SDDMM groups failed: %s", cudaGetErrorString(e));
+    return e == cudaErrorMemoryAllocation ? TCGNN_ERR_OOM : TCGNN_ERR_CUDA;
+  }
+  p->groups = groups;
+  p->num_groups = total;
+  return TCGNN_OK;
+}
+
+int plan_ensure_scratch(tcgnn_plan* p, float** slot, size_t count) {
+  std::lock_guard<std::mutex> lock(p->mu);
+  if (*slot != nullptr) return TCGNN_OK;
+  cudaError_t e = cudaMalloc(slot, sizeof(float) * (count > 0 ? count : 1));
+  if (e != cudaSuccess) {
+    *slot = nullptr;
+    set_last_error("cudaMalloc(scratch) failed: %s", cudaGetErrorString(e));
+    return TCGNN_ERR_OOM;
+  }
+  return TCGNN_OK;
+}
+
+int plan_destroy(tcgnn_plan* p) {
+  if (p == nullptr) return TCGNN_OK;
+  if (p->tiles) cudaFree(p->tiles);
+  if (p->win_tile_ptr) cudaFree(p->win_tile_ptr);
+  if (p->eperm) cudaFree(p->eperm);
+  if (p->weight_perm) cudaFree(p->weight_perm);
+  if (p->sddmm_perm) cudaFree(p->sddmm_perm);
+  if (p->groups) cudaFree(p->groups);
+  if (p->flag) cudaFree(p->flag);
+  delete p;
+  return TCGNN_OK;
+}
+
+}  // namespace tcgnn

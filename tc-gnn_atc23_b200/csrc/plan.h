@@ -1,0 +1,70 @@
+// Host-side plan object behind the opaque `tcgnn_plan` of include/tcgnn_b200.h.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <mutex>
+
+#include "common.cuh"
+
+struct tcgnn_plan {
+  // borrowed device pointers of the caller's graph (must outlive the plan)
+  const int32_t* row_ptr = nullptr;
+  const int32_t* col_idx = nullptr;
+  const int32_t* edge_to_col = nullptr;
+  const int32_t* edge_to_row = nullptr;
+  int32_t num_nodes = 0;
+  int64_t num_edges = 0;
+  int32_t num_windows = 0;
+  int32_t num_tiles = 0;
+  int32_t num_pairs = 0;  // distinct (row, col) pairs == set bits over all tile masks
+  int device = 0;
+  int num_sms = 0;
+  // owned device memory
+  tcgnn::TileMeta* tiles = nullptr;   // [num_tiles + 1]
+  int32_t* win_tile_ptr = nullptr;    // [num_windows + 1]
+  int32_t* eperm = nullptr;           // [num_pairs]   lazy (weighted SpMM / SDDMM)
+  float* weight_perm = nullptr;       // [num_pairs]   lazy: edge weights in tile order
+  float* sddmm_perm = nullptr;        // [num_pairs]   lazy: SDDMM results in tile order
+  int4* groups = nullptr;             // [num_groups]  lazy: SDDMM work units {tile_start, ntiles, win, 0}
+  int32_t num_groups = 0;
+  int32_t* flag = nullptr;            // device error counter
+  std::mutex mu;                      // guards the lazy members
+
+  tcgnn::PlanView view() const {
+    tcgnn::PlanView v;
+    v.tiles = tiles;
+    v.win_tile_ptr = win_tile_ptr;
+    v.eperm = eperm;
+    v.num_nodes = num_nodes;
+    v.num_windows = num_windows;
+    v.num_tiles = num_tiles;
+    v.num_pairs = num_pairs;
+    return v;
+  }
+};
+
+namespace tcgnn {
+
+void set_last_error(const char* fmt, ...);
+void count_launch(int n = 1);
+
+int plan_create(const int32_t* row_ptr, const int32_t* col_idx, const int32_t* block_partition,
+                const int32_t* edge_to_col, const int32_t* edge_to_row, int32_t num_nodes, int64_t num_edges,
+                int32_t num_windows, cudaStream_t stream, tcgnn_plan** plan_out);
+int plan_destroy(tcgnn_plan* plan);
+int plan_ensure_eperm(tcgnn_plan* plan, cudaStream_t stream);
+int plan_ensure_scratch(tcgnn_plan* plan, float** slot, size_t count);
+int plan_ensure_groups(tcgnn_plan* plan, cudaStream_t stream);   // synchronises the stream on first use
+
+// kernels (spmm_tc.cu / sddmm_tc.cu / sgt_gpu.cu / umma_probe.cu)
+int spmm_launch(tcgnn_plan* plan, const float* x, int64_t ldx, const float* edge_weight, float* y, int64_t ldy,
+                int32_t dim, cudaStream_t stream);
+int sddmm_launch(tcgnn_plan* plan, const float* x, int64_t ldx, float* edge_out, int32_t dim, cudaStream_t stream);
+int sgt_cuda(const int32_t* row_ptr, const int32_t* col_idx, int32_t num_nodes, int64_t num_edges, int32_t blk_h,
+             int32_t blk_w, int32_t* block_partition, int32_t* edge_to_col, int32_t* edge_to_row,
+             int64_t* tc_blocks_out, cudaStream_t stream);
+int debug_umma(const void* a_image, int32_t a_bytes, const void* b_image, int32_t b_bytes, uint64_t adesc,
+               uint64_t bdesc, uint32_t idesc, int32_t ksteps, int32_t a_step_bytes, int32_t b_step_bytes,
+               float* d_out, int32_t ncols, cudaStream_t stream);
+
+}  // namespace tcgnn

@@ -1,0 +1,309 @@
+// SDDMM (edge scores) on 5th-gen tensor cores, sm_100a.
+//
+// Replaces sddmm_forward_cuda_kernel of the reference (/root/reference
+// TCGNN_conv/TCGNN_kernel.cu:584-728):  out[e] = sum_k tf32(X[row(e),k]) * tf32(X[col(e),k]).
+// Per row window w and per group of up to 16 TC blocks (= 128 condensed columns) one dense
+// contraction on tcgen05.mma:
+//     S^T (128 gathered cols x 16 window rows) = Xg (128 x D, K-major) . Xw^T (D x 16, K-major)
+//   M = 128 (TMEM lane = condensed column), N = 16 (TMEM column = window row), K = D in steps of 8.
+// Both operands are rows of X, i.e. naturally K-major: the same 128B-swizzled row image serves as
+// A (gathered rows) and as B (the window's own 16 rows).  Only positions that are edges are
+// written (tile occupancy mask), in tile order; a second pass restores CSR edge order.
+//
+// A pipeline stage is one 32-feature chunk of one group: A 16 KB + B 2 KB + the group's 16 tile
+// records (TMA bulk copy).  CTA = 22 warps:
+//   warps 0-3  epilogue     TMEM -> registers -> masked scatter of edge values
+//   warp  4    MMA issuer   warp 5  meta loader (TMA)   warps 6-21  producers (4 groups of 4)
+#include "plan.h"
+
+namespace tcgnn {
+
+namespace {
+
+constexpr int kStages = 10;
+constexpr int kEpiWarps = 4;
+constexpr int kMmaWarp = 4;
+constexpr int kMetaWarp = 5;
+constexpr int kProducerWarp0 = 6;
+constexpr int kProdGroups = 4;
+constexpr int kProdPerGroup = 4;
+constexpr int kWarps = kProducerWarp0 + kProdGroups * kProdPerGroup;
+constexpr int kThreads = kWarps * 32;
+constexpr int kAcc = 4;
+constexpr int kGroupTiles = 16;
+constexpr int kAStageBytes = 128 * 128;                    // 128 rows x 32 floats
+constexpr int kBStageBytes = TCGNN_BLK_H * 128;            // 16 rows x 32 floats
+constexpr int kMetaTileBytes = kGroupTiles * static_cast<int>(sizeof(TileMeta));
+constexpr int kMetaStageBytes = kMetaTileBytes + 16;       // + header {tile_start, ntiles, win, kc}
+constexpr uint32_t kTmemCols = kAcc * 16;
+constexpr int kSmemBytes = kStages * (kAStageBytes + kBStageBytes + kMetaStageBytes) + (3 * kStages + 2 * kAcc) * 8 +
+                           16 + 1024;
+
+// groups [g_lo, g_hi) of this CTA: equal shares of the tile stream, cut at group boundaries
+__device__ __forceinline__ int32_t first_group_at_or_after(const int4* __restrict__ groups, int32_t num_groups,
+                                                           int32_t tile) {
+  int32_t lo = 0, hi = num_groups;
+  while (lo < hi) {
+    const int32_t mid = (lo + hi) >> 1;
+    if (groups[mid].x < tile) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+sddmm_tc_kernel(PlanView pv, const int4* __restrict__ groups, int32_t num_groups, const float* __restrict__ x,
+                int64_t ldx, float* __restrict__ out_perm, int32_t dim, int vec_ok) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* a_smem = smem;
+  uint8_t* b_smem = a_smem + kStages * kAStageBytes;
+  uint8_t* m_smem = b_smem + kStages * kBStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(m_smem + kStages * kMetaStageBytes);
+  uint64_t* meta_full = bars;
+  uint64_t* full = bars + kStages;
+  uint64_t* empty = bars + 2 * kStages;
+  uint64_t* acc_full = bars + 3 * kStages;
+  uint64_t* acc_empty = acc_full + kAcc;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + kAcc);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int64_t nt = pv.num_tiles;
+  const int32_t g_lo = first_group_at_or_after(groups, num_groups, static_cast<int32_t>(nt * blockIdx.x / gridDim.x));
+  const int32_t g_hi =
+      first_group_at_or_after(groups, num_groups, static_cast<int32_t>(nt * (blockIdx.x + 1) / gridDim.x));
+  const int32_t n_groups = g_hi - g_lo;
+  const int32_t nkc = (dim + 31) >> 5;          // 32-feature chunks
+  const int32_t n_stages = n_groups * nkc;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&meta_full[s], 1);
+      mbar_init(&full[s], kProdPerGroup);
+      mbar_init(&empty[s], 1);
+    }
+    for (int b = 0; b < kAcc; ++b) {
+      mbar_init(&acc_full[b], 1);
+      mbar_init(&acc_empty[b], kEpiWarps);
+    }
+    fence_mbar_init();
+  }
+  if (warp == kMmaWarp) tmem_alloc<kTmemCols>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < kEpiWarps) {
+    // ===================================== epilogue =====================================
+    const int q = warp;
+    const int m = q * 32 + lane;       // condensed column inside the group
+    const int tt = m >> 3, c = m & 7;  // tile inside the group, column inside the tile
+    for (int32_t gl = 0; gl < n_groups; ++gl) {
+      const int4 grp = groups[g_lo + gl];
+      uint4 mask = make_uint4(0, 0, 0, 0);
+      int32_t edge_ofs = 0;
+      if (tt < grp.y) {   // issue the record loads before waiting for the accumulator
+        const TileMeta* t = pv.tiles + grp.x + tt;
+        mask = *reinterpret_cast<const uint4*>(t->mask);
+        edge_ofs = t->edge_ofs;
+      }
+      const int b = gl % kAcc;
+      mbar_wait(&acc_full[b], (gl / kAcc) & 1);
+      tc_fence_after();
+      uint32_t v[16];
+      tmem_ld_32x32b_x16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + b * 16, v);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[b]);
+      // bit (r*8+c): word r/4, bit (r%4)*8+c ; rank in bit order = position in tile-ordered output
+      const uint32_t mw[4] = {mask.x, mask.y, mask.z, mask.w};
+      int base_rank = 0;
+#pragma unroll
+      for (int wd = 0; wd < 4; ++wd) {
+#pragma unroll
+        for (int rr = 0; rr < 4; ++rr) {
+          const int bit = rr * 8 + c;
+          if (mw[wd] & (1u << bit)) {
+            const int rank = base_rank + __popc(mw[wd] & ((1u << bit) - 1u));
+            out_perm[edge_ofs + rank] = __uint_as_float(v[wd * 4 + rr]);
+          }
+        }
+        base_rank += __popc(mw[wd]);
+      }
+    }
+  } else if (warp == kMmaWarp) {
+    // ===================================== MMA issuer ===================================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_tf32(128, 16, false, false);
+      // K-major, 128B swizzle: 8-row groups 1024 B apart (SBO); K steps advance the start address by 32 B
+      const uint64_t desc0 = make_smem_desc(0, 16, 1024, kSwizzle128B);
+      for (int32_t k = 0; k < n_stages; ++k) {
+        const int s = k % kStages;
+        const int32_t gl = k / nkc, kc = k - gl * nkc;
+        const int b = gl % kAcc;
+        if (kc == 0) {
+          mbar_wait(&acc_empty[b], ((gl / kAcc) & 1) ^ 1);
+          tc_fence_after();
+        }
+        mbar_wait(&full[s], (k / kStages) & 1);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(a_smem + s * kAStageBytes);
+        const uint32_t b_addr = smem_u32(b_smem + s * kBStageBytes);
+        const int ksteps = min(4, (dim - kc * 32 + 7) >> 3);
+        for (int ks = 0; ks < ksteps; ++ks) {
+          const uint64_t adesc = desc0 | static_cast<uint64_t>(((a_addr + ks * 32) & 0x3FFFFu) >> 4);
+          const uint64_t bdesc = desc0 | static_cast<uint64_t>(((b_addr + ks * 32) & 0x3FFFFu) >> 4);
+          umma_tf32(tmem_base + b * 16, adesc, bdesc, idesc, (kc | ks) != 0 ? 1u : 0u);
+        }
+        umma_commit(&empty[s]);
+        if (kc == nkc - 1) umma_commit(&acc_full[b]);
+      }
+    }
+  } else if (warp == kMetaWarp) {
+    // ===================================== meta loader (TMA) ============================
+    if (lane == 0) {
+      int4 nxt = n_groups > 0 ? groups[g_lo] : make_int4(0, 0, 0, 0);
+      for (int32_t gl = 0; gl < n_groups; ++gl) {
+        const int4 grp = nxt;
+        if (gl + 1 < n_groups) nxt = groups[g_lo + gl + 1];   // prefetch the next work unit
+        for (int32_t kc = 0; kc < nkc; ++kc) {
+          const int32_t k = gl * nkc + kc;
+          const int s = k % kStages;
+          mbar_wait(&empty[s], ((k / kStages) & 1) ^ 1);
+          uint8_t* ms = m_smem + s * kMetaStageBytes;
+          *reinterpret_cast<int4*>(ms + kMetaTileBytes) = make_int4(grp.x, grp.y, grp.z, kc);
+          const uint32_t bytes = static_cast<uint32_t>(grp.y) * sizeof(TileMeta);
+          mbar_arrive_expect_tx(&meta_full[s], bytes);
+          tma_bulk_g2s(ms, pv.tiles + grp.x, bytes, &meta_full[s]);
+        }
+      }
+    }
+  } else {
+    // ===================================== producers ====================================
+    const int p = warp - kProducerWarp0;
+    const int pg = p / kProdPerGroup;    // serves stages k == pg (mod kProdGroups)
+    const int pw = p % kProdPerGroup;
+    constexpr int kRows = 128 + TCGNN_BLK_H;          // gathered rows + the window's own rows
+    constexpr int kItems = kRows * 8;                 // 16-byte vectors per stage
+    constexpr int kPerLane = (kItems + kProdPerGroup * 32 - 1) / (kProdPerGroup * 32);   // 9
+    for (int32_t k = pg; k < n_stages; k += kProdGroups) {
+      const int s = k % kStages;
+      mbar_wait(&meta_full[s], (k / kStages) & 1);
+      const uint8_t* ms = m_smem + s * kMetaStageBytes;
+      const TileMeta* meta = reinterpret_cast<const TileMeta*>(ms);
+      const int4 hdr = *reinterpret_cast<const int4*>(ms + kMetaTileBytes);
+      const int32_t ntiles = hdr.y, win = hdr.z, kc = hdr.w;
+      const int32_t f0 = kc * 32;
+      uint8_t* a_stage = a_smem + s * kAStageBytes;
+      uint8_t* b_stage = b_smem + s * kBStageBytes;
+      float4 val[kPerLane];
+#pragma unroll
+      for (int u = 0; u < kPerLane; ++u) {
+        const int item = u * (kProdPerGroup * 32) + pw * 32 + lane;
+        val[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (item < kItems) {
+          const int row = item >> 3, v = item & 7;
+          int32_t node = -1;
+          if (row < 128) {
+            if ((row >> 3) < ntiles) node = meta[row >> 3].cols[row & 7];
+          } else {
+            node = win * TCGNN_BLK_H + (row - 128);
+            if (node >= pv.num_nodes) node = -1;
+          }
+          const int f = f0 + v * 4;
+          if (node >= 0 && f < dim) {
+            const float* src = x + static_cast<int64_t>(node) * ldx + f;
+            if (vec_ok && f + 4 <= dim) {
+              val[u] = __ldg(reinterpret_cast<const float4*>(src));
+            } else {
+              val[u].x = __ldg(src);
+              if (f + 1 < dim) val[u].y = __ldg(src + 1);
+              if (f + 2 < dim) val[u].z = __ldg(src + 2);
+              if (f + 3 < dim) val[u].w = __ldg(src + 3);
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kPerLane; ++u) {
+        const int item = u * (kProdPerGroup * 32) + pw * 32 + lane;
+        if (item < kItems) {
+          const int row = item >> 3, v = item & 7;
+          uint8_t* dst = row < 128 ? a_stage + (row >> 3) * 1024 + sw128_offset(row & 7, v)
+                                   : b_stage + ((row - 128) >> 3) * 1024 + sw128_offset(row & 7, v);
+          *reinterpret_cast<float4*>(dst) = tf32_rna4(val[u]);
+        }
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full[s]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kMmaWarp) {
+    tc_fence_after();
+    tmem_dealloc<kTmemCols>(tmem_base);
+  }
+}
+
+// tile order -> CSR edge order
+__global__ void unpermute_kernel(const int32_t* __restrict__ eperm, const float* __restrict__ in,
+                                 float* __restrict__ out, int32_t n) {
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    out[eperm[i]] = in[i];
+}
+
+}  // namespace
+
+int sddmm_launch(tcgnn_plan* plan, const float* x, int64_t ldx, float* edge_out, int32_t dim, cudaStream_t stream) {
+  if (plan->num_edges == 0) return TCGNN_OK;
+  int st = plan_ensure_eperm(plan, stream);
+  if (st != TCGNN_OK) return st;
+  st = plan_ensure_groups(plan, stream);
+  if (st != TCGNN_OK) return st;
+  st = plan_ensure_scratch(plan, &plan->sddmm_perm, static_cast<size_t>(plan->num_pairs));
+  if (st != TCGNN_OK) return st;
+  static bool attr_set[64] = {};
+  cudaError_t e;
+  if (plan->device < 64 && !attr_set[plan->device]) {
+    e = cudaFuncSetAttribute(sddmm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    if (e != cudaSuccess) {
+      set_last_error("cudaFuncSetAttribute(sddmm) failed: %s", cudaGetErrorString(e));
+      return TCGNN_ERR_CUDA;
+    }
+    attr_set[plan->device] = true;
+  }
+  int grid = plan->num_sms;
+  if (plan->num_groups < grid * 2) grid = plan->num_groups / 2;
+  if (grid < 1) grid = 1;
+  const int vec_ok = (reinterpret_cast<uintptr_t>(x) % 16 == 0) && (ldx % 4 == 0);
+  if (static_cast<int64_t>(plan->num_pairs) < plan->num_edges) {
+    // duplicated (row, col) pairs: only one edge of each pair receives the value (as in the reference)
+    e = cudaMemsetAsync(edge_out, 0, sizeof(float) * static_cast<size_t>(plan->num_edges), stream);
+    if (e != cudaSuccess) {
+      set_last_error("cudaMemsetAsync failed: %s", cudaGetErrorString(e));
+      return TCGNN_ERR_CUDA;
+    }
+  }
+  sddmm_tc_kernel<<<grid, kThreads, kSmemBytes, stream>>>(plan->view(), plan->groups, plan->num_groups, x, ldx,
+                                                         plan->sddmm_perm, dim, vec_ok);
+  count_launch();
+  int g = (plan->num_pairs + 255) / 256;
+  if (g > 148 * 16) g = 148 * 16;
+  if (g < 1) g = 1;
+  unpermute_kernel<<<g, 256, 0, stream>>>(plan->eperm, plan->sddmm_perm, edge_out, plan->num_pairs);
+  count_launch();
+  e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_last_error("sddmm kernel launch failed: %s", cudaGetErrorString(e));
+    return TCGNN_ERR_CUDA;
+  }
+  return TCGNN_OK;
+}
+
+}  // namespace tcgnn

@@ -1,0 +1,402 @@
+// SpMM (neighbour aggregation) on 5th-gen tensor cores, sm_100a.
+//
+// Replaces spmm_forward_cuda_kernel / spmmAGNN_forward_cuda_kernel of the reference
+// (/root/reference TCGNN_conv/TCGNN_kernel.cu:336-454, :459-578).  Same mathematics, i.e. per
+// 16-row window w and per condensed 16x8 TC block t
+//     Y[16w:16w+16, :] += A_t (16x8, 0/1 or edge weight, tf32) . tf32(X[cols_t, :]) (8xD)
+// but mapped the other way round onto tcgen05.mma so that the gathered feature rows need no
+// transpose:   Yt (D x 16)  +=  Xg^T (D x 8, "MN-major": every gathered row is contiguous along M)
+//                               . A_t^T (8 x 16, K-major)
+//   M = 128 features per MMA (DBLK blocks of 128 per pass), N = 16 window rows, K = 8 neighbours.
+// The accumulator lives in TMEM (lane = feature, column = window row); nothing is rescanned:
+// the plan (plan.cu) delivers, per tile, the 8 rows to gather and a 128-bit occupancy mask.
+//
+// CTA = 24 warps, persistent over a contiguous, equally sized slice of the global tile stream
+// (balances hub windows: a window cut by a slice boundary is combined with fp32 atomics):
+//   warps 0-3   epilogue     TMEM -> registers -> coalesced global stores (lane = feature)
+//   warp  4     MMA issuer   one elected thread issues tcgen05.mma / tcgen05.commit
+//   warp  5     meta loader  TMA bulk copy (UBLKCP) of the stage's tile records into smem
+//   warps 6-7   B builders   expand occupancy masks (or edge weights) into the K-major B tile
+//   warps 8-23  A producers  128-bit coalesced gathers of X rows, cvt.rna.tf32 in registers,
+//                            st.shared into the 128B-swizzled MN-major A tile
+// Pipeline: S stages of G=4 tiles; per stage three mbarriers (meta_full, full, empty); NACC
+// TMEM accumulators with acc_full / acc_empty so the epilogue overlaps the next windows.
+#include "plan.h"
+
+namespace tcgnn {
+
+namespace {
+
+constexpr int kG = 4;                 // tiles per pipeline stage
+constexpr int kEpiWarps = 4;
+constexpr int kMmaWarp = 4;
+constexpr int kMetaWarp = 5;
+constexpr int kBuilderWarp0 = 6;
+constexpr int kBuilders = 2;
+constexpr int kProducerWarp0 = 8;
+constexpr int kProducers = 16;        // 4 groups of kG warps; group i serves stages k == i (mod 4)
+constexpr int kProducerGroups = kProducers / kG;
+constexpr int kWarps = kProducerWarp0 + kProducers;
+constexpr int kThreads = kWarps * 32;
+constexpr int kAcc = 4;               // TMEM accumulator ring
+constexpr int kBTileBytes = TCGNN_BLK_H * TCGNN_BLK_W * 4;  // 512
+constexpr int kMetaStageBytes = kG * static_cast<int>(sizeof(TileMeta));
+
+template <int DBLK>
+struct Cfg {
+  static constexpr int kATileBytes = DBLK * 4096;              // DBLK*4 swizzle atoms of 8 rows x 128 B
+  static constexpr int kAStageBytes = kG * kATileBytes;
+  static constexpr int kBStageBytes = kG * kBTileBytes;
+  static constexpr int kStages = DBLK == 1 ? 10 : 6;
+  static constexpr uint32_t kTmemCols = kAcc * DBLK * 16;      // 64 / 128
+  static constexpr int kSmemBytes = kStages * (kAStageBytes + kBStageBytes + kMetaStageBytes) +
+                                    (3 * kStages + 2 * kAcc) * 8 + 16 + 1024 /*alignment slack*/;
+};
+
+struct SliceInfo {
+  int32_t t0, t1;        // tile range of this CTA
+  int32_t w_first;       // window of tile t0
+  int32_t n_windows;     // windows touched
+  bool partial_first;    // first window starts before t0  -> atomics
+  bool partial_last;     // last window ends after t1      -> atomics
+};
+
+__device__ __forceinline__ void slice_range(int32_t num_tiles, int32_t& t0, int32_t& t1) {
+  const int64_t nt = num_tiles;
+  t0 = static_cast<int32_t>(nt * blockIdx.x / gridDim.x);
+  t1 = static_cast<int32_t>(nt * (blockIdx.x + 1) / gridDim.x);
+}
+
+__device__ __forceinline__ SliceInfo slice_info(const PlanView& pv) {
+  SliceInfo s;
+  slice_range(pv.num_tiles, s.t0, s.t1);
+  s.w_first = 0;
+  s.n_windows = 0;
+  s.partial_first = s.partial_last = false;
+  if (s.t1 > s.t0) {
+    const TileMeta* a = pv.tiles + s.t0;
+    const TileMeta* b = pv.tiles + (s.t1 - 1);
+    s.w_first = a->win;
+    s.n_windows = b->win - a->win + 1;
+    s.partial_first = (a->flags & kTileFirst) == 0;
+    s.partial_last = (b->flags & kTileLast) == 0;
+  }
+  return s;
+}
+
+// Rows of windows cut by a slice boundary are accumulated with atomics: clear them first.
+__global__ void spmm_zero_partial_rows(PlanView pv, float* __restrict__ y, int64_t ldy, int32_t dim) {
+  const SliceInfo s = slice_info(pv);
+  if (s.t1 <= s.t0) return;
+  for (int side = 0; side < 2; ++side) {
+    const bool partial = side == 0 ? s.partial_first : s.partial_last;
+    if (!partial) continue;
+    if (side == 1 && s.n_windows == 1 && s.partial_first) continue;  // same window, already cleared
+    const int32_t w = side == 0 ? s.w_first : s.w_first + s.n_windows - 1;
+    const int32_t row0 = w * TCGNN_BLK_H;
+    const int32_t rows = min(TCGNN_BLK_H, pv.num_nodes - row0);
+    for (int i = threadIdx.x; i < rows * dim; i += blockDim.x) y[(row0 + i / dim) * ldy + i % dim] = 0.0f;
+  }
+}
+
+// Edge weights (CSR order) -> tile order, rounded to tf32 like the reference (TCGNN_kernel.cu:560-563).
+__global__ void permute_weights_kernel(const int32_t* __restrict__ eperm, const float* __restrict__ w,
+                                       float* __restrict__ out, int32_t n) {
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    out[i] = tf32_rna(w[eperm[i]]);
+}
+
+template <int DBLK>
+__global__ void __launch_bounds__(kThreads, 1)
+spmm_tc_kernel(PlanView pv, const float* __restrict__ x, int64_t ldx, const float* __restrict__ wperm,
+               float* __restrict__ y, int64_t ldy, int32_t dim /* <= DBLK*128, features of this pass */,
+               int vec_ok /* x 16B-aligned and ldx % 4 == 0 */) {
+  using C = Cfg<DBLK>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* a_smem = smem;                                              // [S][G][DBLK*4 atoms][8][128B]
+  uint8_t* b_smem = a_smem + C::kStages * C::kAStageBytes;             // [S][G][512B]
+  uint8_t* m_smem = b_smem + C::kStages * C::kBStageBytes;             // [S][G] TileMeta
+  uint64_t* bars = reinterpret_cast<uint64_t*>(m_smem + C::kStages * kMetaStageBytes);
+  uint64_t* meta_full = bars;
+  uint64_t* full = bars + C::kStages;
+  uint64_t* empty = bars + 2 * C::kStages;
+  uint64_t* acc_full = bars + 3 * C::kStages;
+  uint64_t* acc_empty = acc_full + kAcc;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + kAcc);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const SliceInfo sl = slice_info(pv);
+  const int32_t n_tiles = sl.t1 - sl.t0;
+  const int32_t n_stages = (n_tiles + kG - 1) / kG;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < C::kStages; ++s) {
+      mbar_init(&meta_full[s], 1);
+      mbar_init(&full[s], kG + 1);   // kG producer warps + 1 builder warp
+      mbar_init(&empty[s], 1);       // tcgen05.commit
+    }
+    for (int b = 0; b < kAcc; ++b) {
+      mbar_init(&acc_full[b], 1);            // tcgen05.commit
+      mbar_init(&acc_empty[b], kEpiWarps);   // one arrive per epilogue warp
+    }
+    fence_mbar_init();
+  }
+  if (warp == kMmaWarp) tmem_alloc<C::kTmemCols>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < kEpiWarps) {
+    // ===================================== epilogue =====================================
+    const int q = warp;  // TMEM lane quadrant == warp id % 4
+    for (int32_t wl = 0; wl < sl.n_windows; ++wl) {
+      const int b = wl % kAcc;
+      mbar_wait(&acc_full[b], (wl / kAcc) & 1);
+      tc_fence_after();
+      const int32_t w = sl.w_first + wl;
+      const bool use_atomic = (wl == 0 && sl.partial_first) || (wl == sl.n_windows - 1 && sl.partial_last);
+      const int32_t row0 = w * TCGNN_BLK_H;
+#pragma unroll
+      for (int m = 0; m < DBLK; ++m) {
+        const int f = m * 128 + q * 32 + lane;       // feature owned by this thread
+        if (m * 128 + q * 32 < dim) {                // warp-uniform
+          uint32_t v[16];
+          tmem_ld_32x32b_x16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (b * DBLK + m) * 16, v);
+          tmem_ld_wait();
+          if (f < dim) {
+            float* yp = y + static_cast<int64_t>(row0) * ldy + f;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              if (row0 + i < pv.num_nodes) {
+                if (use_atomic) atomicAdd(yp + i * ldy, __uint_as_float(v[i]));
+                else yp[i * ldy] = __uint_as_float(v[i]);
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[b]);
+    }
+  } else if (warp == kMmaWarp) {
+    // ===================================== MMA issuer ===================================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_tf32(128, 16, /*A MN-major*/ true, /*B K-major*/ false);
+      // A: MN-major, 128B swizzle: 32-feature atoms 1024 B apart (LBO); a K=8 MMA spans one atom row group
+      const uint64_t adesc0 = make_smem_desc(0, 1024, 1024, kSwizzle128B);
+      // B: K-major, no swizzle: 8x16B core matrices; K chunks 128 B apart (LBO), 8-row groups 256 B apart (SBO)
+      const uint64_t bdesc0 = make_smem_desc(0, 128, 256, kSwizzleNone);
+      int32_t wl = 0;
+      int b = 0;
+      for (int32_t k = 0; k < n_stages; ++k) {
+        const int s = k % C::kStages;
+        mbar_wait(&full[s], (k / C::kStages) & 1);
+        tc_fence_after();
+        const TileMeta* meta = reinterpret_cast<const TileMeta*>(m_smem + s * kMetaStageBytes);
+        const int32_t g0 = sl.t0 + k * kG;
+        const int nt = min(kG, sl.t1 - g0);
+        for (int j = 0; j < nt; ++j) {
+          const uint32_t flags = meta[j].flags;
+          const bool first = (flags & kTileFirst) != 0 || (g0 + j == sl.t0);
+          const bool last = (flags & kTileLast) != 0 || (g0 + j == sl.t1 - 1);
+          if (first) {
+            b = wl % kAcc;
+            mbar_wait(&acc_empty[b], ((wl / kAcc) & 1) ^ 1);
+            tc_fence_after();
+          }
+          const uint32_t a_addr = smem_u32(a_smem + s * C::kAStageBytes + j * C::kATileBytes);
+          const uint32_t b_addr = smem_u32(b_smem + s * C::kBStageBytes + j * kBTileBytes);
+          const uint64_t bdesc = bdesc0 | static_cast<uint64_t>((b_addr & 0x3FFFFu) >> 4);
+#pragma unroll
+          for (int m = 0; m < DBLK; ++m) {
+            const uint64_t adesc = adesc0 | static_cast<uint64_t>(((a_addr + m * 4096) & 0x3FFFFu) >> 4);
+            umma_tf32(tmem_base + (b * DBLK + m) * 16, adesc, bdesc, idesc, first ? 0u : 1u);
+          }
+          if (last) {
+            umma_commit(&acc_full[b]);
+            ++wl;
+          }
+        }
+        umma_commit(&empty[s]);
+      }
+    }
+  } else if (warp == kMetaWarp) {
+    // ===================================== meta loader (TMA) ============================
+    if (lane == 0) {
+      for (int32_t k = 0; k < n_stages; ++k) {
+        const int s = k % C::kStages;
+        mbar_wait(&empty[s], ((k / C::kStages) & 1) ^ 1);
+        const int32_t g0 = sl.t0 + k * kG;
+        const uint32_t bytes = static_cast<uint32_t>(min(kG, sl.t1 - g0)) * sizeof(TileMeta);
+        mbar_arrive_expect_tx(&meta_full[s], bytes);
+        tma_bulk_g2s(m_smem + s * kMetaStageBytes, pv.tiles + g0, bytes, &meta_full[s]);
+      }
+    }
+  } else if (warp < kProducerWarp0) {
+    // ===================================== B builders ===================================
+    const int bq = warp - kBuilderWarp0;
+    // lane -> 16-byte chunk `lane` of the tile: [n/8][k/4][n%8] x 4 floats (k%4)
+    const int n = (lane >> 4) * 8 + (lane & 7);
+    const int kq = (lane >> 3) & 1;
+    const int word = n >> 2;
+    const int shift = (n & 3) * 8 + kq * 4;
+    for (int32_t k = bq; k < n_stages; k += kBuilders) {
+      const int s = k % C::kStages;
+      mbar_wait(&meta_full[s], (k / C::kStages) & 1);
+      const TileMeta* meta = reinterpret_cast<const TileMeta*>(m_smem + s * kMetaStageBytes);
+      const int nt = min(kG, sl.t1 - (sl.t0 + k * kG));
+      float4 v[kG];
+#pragma unroll
+      for (int j = 0; j < kG; ++j) {   // all loads of the stage first (weighted path: up to 16 in flight)
+        v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (j < nt) {
+          const uint32_t mw = meta[j].mask[word];
+          const uint32_t nib = (mw >> shift) & 0xFu;
+          if (wperm == nullptr) {
+            v[j].x = (nib & 1u) ? 1.0f : 0.0f;
+            v[j].y = (nib & 2u) ? 1.0f : 0.0f;
+            v[j].z = (nib & 4u) ? 1.0f : 0.0f;
+            v[j].w = (nib & 8u) ? 1.0f : 0.0f;
+          } else if (nib != 0u) {
+            // rank of the first of my four bits among the tile's set bits (bit order r*8+c)
+            int rank = __popc(mw & ((1u << shift) - 1u));
+            for (int i = 0; i < word; ++i) rank += __popc(meta[j].mask[i]);
+            const float* wp = wperm + meta[j].edge_ofs + rank;
+            if (nib & 1u) v[j].x = __ldg(wp++);
+            if (nib & 2u) v[j].y = __ldg(wp++);
+            if (nib & 4u) v[j].z = __ldg(wp++);
+            if (nib & 8u) v[j].w = __ldg(wp++);
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < kG; ++j)
+        if (j < nt) *reinterpret_cast<float4*>(b_smem + s * C::kBStageBytes + j * kBTileBytes + lane * 16) = v[j];
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full[s]);
+    }
+  } else {
+    // ===================================== A producers ==================================
+    const int p = warp - kProducerWarp0;
+    const int grp = p / kG;   // serves stages k == grp (mod kProducerGroups)
+    const int j = p % kG;     // tile slot inside the stage
+    const int nvec = (dim + 3) >> 2;          // 16-byte vectors per feature row in this pass
+    const int nvec_shift = (nvec & (nvec - 1)) == 0 ? __ffs(nvec) - 1 : -1;   // power of two: shift, no division
+    for (int32_t k = grp; k < n_stages; k += kProducerGroups) {
+      const int s = k % C::kStages;
+      mbar_wait(&meta_full[s], (k / C::kStages) & 1);
+      const int nt = min(kG, sl.t1 - (sl.t0 + k * kG));
+      if (j < nt) {
+        const TileMeta* meta = reinterpret_cast<const TileMeta*>(m_smem + s * kMetaStageBytes) + j;
+        uint8_t* a_tile = a_smem + s * C::kAStageBytes + j * C::kATileBytes;
+        const int items = 8 * nvec;           // (row r, vector v) pairs, r-major
+        for (int base = 0; base < items; base += 8 * 32) {
+          float4 val[8];
+          int it[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int item = base + u * 32 + lane;
+            it[u] = item;
+            val[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (item < items) {
+              const int r = nvec_shift >= 0 ? item >> nvec_shift : item / nvec;
+              const int v = item - r * nvec;
+              const int32_t col = meta->cols[r];
+              if (col >= 0) {
+                const float* src = x + static_cast<int64_t>(col) * ldx + v * 4;
+                if (vec_ok && v * 4 + 4 <= dim) {
+                  val[u] = __ldg(reinterpret_cast<const float4*>(src));
+                } else {
+                  if (v * 4 + 0 < dim) val[u].x = __ldg(src + 0);
+                  if (v * 4 + 1 < dim) val[u].y = __ldg(src + 1);
+                  if (v * 4 + 2 < dim) val[u].z = __ldg(src + 2);
+                  if (v * 4 + 3 < dim) val[u].w = __ldg(src + 3);
+                }
+              }
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int item = it[u];
+            if (item < items) {
+              const int r = nvec_shift >= 0 ? item >> nvec_shift : item / nvec;
+              const int v = item - r * nvec;
+              *reinterpret_cast<float4*>(a_tile + (v >> 3) * 1024 + sw128_offset(r, v & 7)) = tf32_rna4(val[u]);
+            }
+          }
+        }
+        fence_proxy_async_smem();
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full[s]);
+    }
+  }
+
+  // ===================================== teardown =======================================
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kMmaWarp) {
+    tc_fence_after();
+    tmem_dealloc<C::kTmemCols>(tmem_base);
+  }
+}
+
+template <int DBLK>
+cudaError_t launch_pass(const tcgnn_plan* plan, int grid, const float* x, int64_t ldx, const float* wperm, float* y,
+                        int64_t ldy, int32_t dim, cudaStream_t stream) {
+  using C = Cfg<DBLK>;
+  static bool attr_set[64] = {};
+  const int dev = plan->device;
+  if (dev < 64 && !attr_set[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(spmm_tc_kernel<DBLK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         C::kSmemBytes);
+    if (e != cudaSuccess) return e;
+    attr_set[dev] = true;
+  }
+  const int vec_ok = (reinterpret_cast<uintptr_t>(x) % 16 == 0) && (ldx % 4 == 0);
+  spmm_zero_partial_rows<<<grid, 128, 0, stream>>>(plan->view(), y, ldy, dim);
+  count_launch();
+  spmm_tc_kernel<DBLK><<<grid, kThreads, C::kSmemBytes, stream>>>(plan->view(), x, ldx, wperm, y, ldy, dim, vec_ok);
+  count_launch();
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+int spmm_launch(tcgnn_plan* plan, const float* x, int64_t ldx, const float* edge_weight, float* y, int64_t ldy,
+                int32_t dim, cudaStream_t stream) {
+  const float* wperm = nullptr;
+  if (edge_weight != nullptr && plan->num_pairs > 0) {
+    int st = plan_ensure_eperm(plan, stream);
+    if (st != TCGNN_OK) return st;
+    st = plan_ensure_scratch(plan, &plan->weight_perm, static_cast<size_t>(plan->num_pairs));
+    if (st != TCGNN_OK) return st;
+    int g = (plan->num_pairs + 255) / 256;
+    if (g > 148 * 16) g = 148 * 16;
+    permute_weights_kernel<<<g, 256, 0, stream>>>(plan->eperm, edge_weight, plan->weight_perm, plan->num_pairs);
+    count_launch();
+    wperm = plan->weight_perm;
+  }
+  // one CTA per SM, each owning an equal slice of the tile stream (>= 8 tiles per CTA)
+  int grid = plan->num_sms;
+  if (plan->num_tiles < grid * 8) grid = plan->num_tiles / 8;
+  if (grid < 1) grid = 1;
+  for (int32_t f0 = 0; f0 < dim; f0 += 256) {
+    const int32_t d = dim - f0 < 256 ? dim - f0 : 256;
+    cudaError_t e = d > 128 ? launch_pass<2>(plan, grid, x + f0, ldx, wperm, y + f0, ldy, d, stream)
+                            : launch_pass<1>(plan, grid, x + f0, ldx, wperm, y + f0, ldy, d, stream);
+    if (e != cudaSuccess) {
+      set_last_error("spmm kernel launch failed: %s", cudaGetErrorString(e));
+      return TCGNN_ERR_CUDA;
+    }
+  }
+  return TCGNN_OK;
+}
+
+}  // namespace tcgnn

@@ -1,0 +1,108 @@
+// Layout probe: one CTA, caller-supplied shared-memory images and UMMA descriptors, returns the
+// raw TMEM accumulator.  tests/test_gpu_umma_layouts.py uses it to pin, on real hardware, every
+// shared-memory layout / descriptor encoding the production kernels rely on (MN-major 128B-swizzled
+// tf32 A tiles, K-major B tiles, the 32-byte K advance inside a swizzle atom, TMEM lane mapping).
+#include <vector>
+
+#include "plan.h"
+
+namespace tcgnn {
+
+namespace {
+
+constexpr int kProbeMaxA = 96 * 1024;
+constexpr int kProbeMaxB = 32 * 1024;
+
+__global__ void __launch_bounds__(128, 1)
+umma_probe_kernel(const uint8_t* __restrict__ a_img, int a_bytes, const uint8_t* __restrict__ b_img, int b_bytes,
+                  uint64_t adesc, uint64_t bdesc, uint32_t idesc, int ksteps, int a_step, int b_step,
+                  float* __restrict__ d_out, int ncols) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* a_smem = smem;
+  uint8_t* b_smem = smem + kProbeMaxA;
+  __shared__ uint64_t done_bar;
+  __shared__ uint32_t tmem_slot;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  for (int i = threadIdx.x; i < a_bytes / 16; i += blockDim.x)
+    reinterpret_cast<uint4*>(a_smem)[i] = reinterpret_cast<const uint4*>(a_img)[i];
+  for (int i = threadIdx.x; i < b_bytes / 16; i += blockDim.x)
+    reinterpret_cast<uint4*>(b_smem)[i] = reinterpret_cast<const uint4*>(b_img)[i];
+  if (threadIdx.x == 0) {
+    mbar_init(&done_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc<64>(&tmem_slot);
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+
+  if (threadIdx.x == 0) {
+    const uint32_t a_addr = smem_u32(a_smem), b_addr = smem_u32(b_smem);
+    for (int k = 0; k < ksteps; ++k) {
+      const uint64_t ad = adesc + static_cast<uint64_t>(((a_addr + k * a_step) & 0x3FFFFu) >> 4);
+      const uint64_t bd = bdesc + static_cast<uint64_t>(((b_addr + k * b_step) & 0x3FFFFu) >> 4);
+      umma_tf32(tmem_base, ad, bd, idesc, k > 0 ? 1u : 0u);
+    }
+    umma_commit(&done_bar);
+  }
+  mbar_wait(&done_bar, 0);
+  tc_fence_after();
+  for (int c0 = 0; c0 < ncols; c0 += 16) {
+    uint32_t v[16];
+    tmem_ld_32x32b_x16(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + c0, v);
+    tmem_ld_wait();
+    for (int i = 0; i < 16; ++i) d_out[(warp * 32 + lane) * ncols + c0 + i] = __uint_as_float(v[i]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc<64>(tmem_base);
+  }
+}
+
+}  // namespace
+
+int debug_umma(const void* a_image, int32_t a_bytes, const void* b_image, int32_t b_bytes, uint64_t adesc,
+               uint64_t bdesc, uint32_t idesc, int32_t ksteps, int32_t a_step_bytes, int32_t b_step_bytes,
+               float* d_out, int32_t ncols, cudaStream_t stream) {
+  if (a_image == nullptr || b_image == nullptr || d_out == nullptr || a_bytes <= 0 || b_bytes <= 0 ||
+      a_bytes % 16 != 0 || b_bytes % 16 != 0 || a_bytes > kProbeMaxA || b_bytes > kProbeMaxB || ksteps < 1 ||
+      (ncols != 16 && ncols != 32 && ncols != 64)) {
+    set_last_error("tcgnn_debug_umma: bad argument");
+    return TCGNN_ERR_INVALID_ARG;
+  }
+  uint8_t *da = nullptr, *db = nullptr;
+  float* dd = nullptr;
+  int status = TCGNN_ERR_CUDA;
+  const int smem_bytes = kProbeMaxA + kProbeMaxB + 1024;
+  cudaError_t e;
+  if ((e = cudaMalloc(&da, a_bytes)) != cudaSuccess) goto done;
+  if ((e = cudaMalloc(&db, b_bytes)) != cudaSuccess) goto done;
+  if ((e = cudaMalloc(&dd, sizeof(float) * 128 * ncols)) != cudaSuccess) goto done;
+  if ((e = cudaMemcpyAsync(da, a_image, a_bytes, cudaMemcpyHostToDevice, stream)) != cudaSuccess) goto done;
+  if ((e = cudaMemcpyAsync(db, b_image, b_bytes, cudaMemcpyHostToDevice, stream)) != cudaSuccess) goto done;
+  if ((e = cudaFuncSetAttribute(umma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes)) !=
+      cudaSuccess)
+    goto done;
+  umma_probe_kernel<<<1, 128, smem_bytes, stream>>>(da, a_bytes, db, b_bytes, adesc, bdesc, idesc, ksteps,
+                                                    a_step_bytes, b_step_bytes, dd, ncols);
+  count_launch();
+  if ((e = cudaGetLastError()) != cudaSuccess) goto done;
+  if ((e = cudaMemcpyAsync(d_out, dd, sizeof(float) * 128 * ncols, cudaMemcpyDeviceToHost, stream)) != cudaSuccess)
+    goto done;
+  if ((e = cudaStreamSynchronize(stream)) != cudaSuccess) goto done;
+  status = TCGNN_OK;
+done:
+  if (status != TCGNN_OK) set_last_error("tcgnn_debug_umma: %s", cudaGetErrorString(e));
+  if (da) cudaFree(da);
+  if (db) cudaFree(db);
+  if (dd) cudaFree(dd);
+  return status;
+}
+
+}  // namespace tcgnn

@@ -1,0 +1,130 @@
+"""SpMM parity on the GPU, through the C ABI (tcgnn_plan_create + tcgnn_spmm_f32) and through the
+`TCGNN.forward` / `TCGNN.forward_AGNN` operators.
+
+Tolerances (floating point, stated per north star): the reference rounds operands to TF32 with RNA
+and accumulates in fp32 (TCGNN_kernel.cu:436-446); against the oracle that emulates exactly that,
+only the accumulation order differs -> |d| <= 1e-5 * sum|terms|.  Against fp64 "true math" the TF32
+rounding itself shows -> |d| <= 1e-3 * sum|terms| (the 1e-3 relative bound of the north star)."""
+import numpy as np
+import pytest
+
+import tcgnn_oracle as orc
+from _util import assert_normwise, features, small_graphs, sgt_arrays, to_dev, load_golden, GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+GRAPHS = small_graphs()
+IDS = [g[0] for g in GRAPHS]
+
+
+def run_spmm(rp, ci, n, x, w=None, via="capi"):
+    import torch
+    import tcgnn_capi
+    bp, e2c, e2r = sgt_arrays(rp, ci, n)
+    d_rp, d_ci, d_bp, d_e2c, d_e2r, d_x = to_dev(rp, ci, bp, e2c, e2r, x)
+    d_w = None if w is None else to_dev(w)[0]
+    if via == "capi":
+        plan = tcgnn_capi.Plan(d_rp, d_ci, d_bp, d_e2c, d_e2r)
+        y = torch.full_like(d_x, float("nan"))   # the op must overwrite every element
+        plan.spmm(d_x, y, d_w)
+        torch.cuda.synchronize()
+        out = y.cpu().numpy()
+        plan.close()
+        return out
+    import TCGNN
+    if w is None:
+        y = TCGNN.forward(d_x, d_rp, d_ci, d_bp, d_e2c, d_e2r)[0]
+    else:
+        y = TCGNN.forward_AGNN(d_x, d_rp, d_ci, d_w.reshape(1, -1).contiguous(), d_bp, d_e2c, d_e2r)[0]
+    torch.cuda.synchronize()
+    return y.cpu().numpy()
+
+
+@pytest.mark.parametrize("graph", GRAPHS, ids=IDS)
+@pytest.mark.parametrize("dim", [16, 128])
+def test_spmm_matches_oracle(graph, dim):
+    name, rp, ci, n = graph
+    x = features(n, dim, seed=3)
+    got = run_spmm(rp, ci, n, x)
+    scale = orc.spmm_abs(x, rp, ci)
+    assert_normwise(got, orc.spmm(x, rp, ci), scale, 1e-5, f"{name} D={dim} vs tf32 oracle")
+    assert_normwise(got, orc.spmm(x, rp, ci, tf32=False, dtype=np.float64), scale, 1e-3, f"{name} D={dim} vs fp64")
+
+
+@pytest.mark.parametrize("dim", [1, 7, 22, 32, 64, 96, 100, 256, 300, 520])
+def test_spmm_feature_widths(dim):
+    """D % 16 != 0, D > 128 (the reference leaves these columns at zero), D > 256
+    (several passes), unaligned rows (D % 4 != 0 -> scalar gather path)."""
+    rp, ci = orc.rmat_graph(3000, 60000, seed=5)
+    x = features(3000, dim, seed=4)
+    got = run_spmm(rp, ci, 3000, x)
+    assert_normwise(got, orc.spmm(x, rp, ci), orc.spmm_abs(x, rp, ci), 1e-5, f"D={dim}")
+
+
+@pytest.mark.parametrize("name", ["kat_n500", "kat_n2000"])
+def test_spmm_known_answer_fixtures(name):
+    """The reference's own fixtures: X = ones -> degree (gnn_conv.py:61), X[i,:] = i -> sum of
+    neighbour ids (gnn_conv.py:13-23).  Small integers: exact in TF32/fp32 -> bit-exact."""
+    g = load_golden(f"{GOLDEN}/{name}.npz")
+    rp, ci, n = g["row_pointers"], g["column_index"], int(g["num_nodes"])
+    got = run_spmm(rp, ci, n, np.ones((n, 32), np.float32))
+    assert np.array_equal(got, np.repeat(g["degree"].astype(np.float32)[:, None], 32, 1))
+    xi = np.repeat(np.arange(n, dtype=np.float32)[:, None], 16, 1)
+    got = run_spmm(rp, ci, n, xi, via="module")
+    assert np.array_equal(got, np.repeat(g["neighbour_id_sum"].astype(np.float32)[:, None], 16, 1))
+
+
+@pytest.mark.parametrize("graph", GRAPHS, ids=IDS)
+def test_weighted_spmm_matches_oracle(graph):
+    name, rp, ci, n = graph
+    if name == "unsorted_dups_n200":
+        pytest.skip("duplicated (row, col) pairs: the reference's weighted kernel is a last-writer-wins race")
+    x = features(n, 64, seed=6)
+    w = np.random.default_rng(7).standard_normal(len(ci)).astype(np.float32)
+    got = run_spmm(rp, ci, n, x, w, via="module")
+    scale = orc.spmm_abs(x, rp, ci, w)
+    assert_normwise(got, orc.spmm(x, rp, ci, w), scale, 1e-5, f"{name} weighted vs tf32 oracle")
+    assert_normwise(got, orc.spmm(x, rp, ci, w, tf32=False, dtype=np.float64), scale, 2e-3, f"{name} weighted vs fp64")
+
+
+def test_spmm_exact_on_integers_with_hub_splits():
+    """Integer features: every partial sum is exact, so atomically combined slices (windows cut by
+    CTA slice boundaries, hub rows) must reproduce the oracle bit for bit."""
+    n = 4000
+    rng = np.random.default_rng(8)
+    src = np.concatenate([np.full(3500, 17), rng.integers(0, n, 30000)])
+    dst = np.concatenate([rng.choice(n, 3500, replace=False), rng.integers(0, n, 30000)])
+    rp, ci = orc.csr_from_edges(src, dst, n)
+    x = features(n, 128, seed=9, kind="ints")
+    got = run_spmm(rp, ci, n, x)
+    assert np.array_equal(got, orc.spmm(x, rp, ci))
+
+
+def test_spmm_linearity_and_strided_views():
+    """Size-independent properties on a mid-size graph: SpMM(2X) == 2 SpMM(X) exactly, column slices
+    of a wider matrix (ldx > dim) give the same columns."""
+    import torch
+    import tcgnn_capi
+    n = 50000
+    rp, ci = orc.rmat_graph(n, 2_000_000, seed=10)
+    bp, e2c, e2r = sgt_arrays(rp, ci, n)
+    x = features(n, 160, seed=11)
+    d_rp, d_ci, d_bp, d_e2c, d_e2r, d_x = to_dev(rp, ci, bp, e2c, e2r, x)
+    plan = tcgnn_capi.Plan(d_rp, d_ci, d_bp, d_e2c, d_e2r)
+    y1 = torch.empty_like(d_x)
+    y2 = torch.empty_like(d_x)
+    plan.spmm(d_x, y1)
+    plan.spmm(d_x * 2, y2)
+    assert torch.equal(y1 * 2, y2)
+    ys = torch.empty(n, 64, device="cuda")
+    plan.spmm(d_x[:, 32:96], ys, dim=64)          # ldx = 160, dim = 64, 16-byte aligned offset
+    torch.cuda.synchronize()
+    ref = torch.empty(n, 64, device="cuda")
+    plan.spmm(d_x[:, 32:96].contiguous(), ref)
+    assert torch.equal(ys, ref)
+    deg = torch.from_numpy(np.diff(rp).astype(np.float32)).cuda()
+    ones = torch.ones(n, 16, device="cuda")
+    yo = torch.empty_like(ones)
+    plan.spmm(ones, yo)
+    assert torch.equal(yo, deg[:, None].expand(-1, 16))
+    plan.close()
