@@ -176,7 +176,7 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // ---------------------------------------------------------------------------------------------
 // Shared-memory matrix descriptor: start address, leading/stride byte offsets (all >>4),
 // descriptor version 1 (Blackwell) at bits [46,48), swizzle mode at bits [61,64).
-constexpr uint64_t kSwizzleNone = 0, kSwizzle128B = 2;
+constexpr uint64_t kSwizzleNone = 0, kSwizzle128BBase32B = 1, kSwizzle128B = 2;
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
                                                    uint64_t swizzle) {
   uint64_t d = 0;
@@ -200,6 +200,13 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(uint32_t m, uint32_t n, b
 // 128B-swizzle atom whose base is 1024-byte aligned (chunk index XOR row, Swizzle<3,4,3>).
 __device__ __forceinline__ uint32_t sw128_offset(uint32_t row, uint32_t chunk16) {
   return row * 128u + ((chunk16 ^ (row & 7u)) << 4);
+}
+
+// Same rows, but the 32-byte swizzle granule of SWIZZLE_128B_BASE32B (Swizzle<2,5,2>: address bits
+// [5,7) ^= bits [7,9)), the only shared-memory layout tcgen05 accepts for MN-major tf32 operands.
+// `row` is the 128-byte row inside a 512-byte aligned atom of 4 rows (8 rows = two stacked atoms).
+__device__ __forceinline__ uint32_t sw128_base32_offset(uint32_t row, uint32_t chunk16) {
+  return row * 128u + ((chunk16 ^ ((row & 3u) << 1)) << 4);
 }
 
 }  // namespace tcgnn

@@ -160,6 +160,8 @@ sddmm_tc_kernel(PlanView pv, const int4* __restrict__ groups, int32_t num_groups
         umma_commit(&empty[s]);
         if (kc == nkc - 1) umma_commit(&acc_full[b]);
       }
+      // the last commit must land in this CTA's shared memory before the CTA may retire
+      if (n_stages > 0) mbar_wait(&empty[(n_stages - 1) % kStages], ((n_stages - 1) / kStages) & 1);
     }
   } else if (warp == kMetaWarp) {
     // ===================================== meta loader (TMA) ============================

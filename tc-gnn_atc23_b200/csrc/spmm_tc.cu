@@ -18,7 +18,7 @@
 //   warp  5     meta loader  TMA bulk copy (UBLKCP) of the stage's tile records into smem
 //   warps 6-7   B builders   expand occupancy masks (or edge weights) into the K-major B tile
 //   warps 8-23  A producers  128-bit coalesced gathers of X rows, cvt.rna.tf32 in registers,
-//                            st.shared into the 128B-swizzled MN-major A tile
+//                            st.shared into the swizzled (128B rows, 32B granule) MN-major A tile
 // Pipeline: S stages of G=4 tiles; per stage three mbarriers (meta_full, full, empty); NACC
 // TMEM accumulators with acc_full / acc_empty so the epilogue overlaps the next windows.
 #include "plan.h"
@@ -187,8 +187,9 @@ spmm_tc_kernel(PlanView pv, const float* __restrict__ x, int64_t ldx, const floa
     // ===================================== MMA issuer ===================================
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_tf32(128, 16, /*A MN-major*/ true, /*B K-major*/ false);
-      // A: MN-major, 128B swizzle: 32-feature atoms 1024 B apart (LBO); a K=8 MMA spans one atom row group
-      const uint64_t adesc0 = make_smem_desc(0, 1024, 1024, kSwizzle128B);
+      // A: MN-major tf32 -> SWIZZLE_128B_BASE32B atoms of 32 features x 4 k-rows (4 x 128 B): feature blocks
+      // 1024 B apart (LBO), the two k-halves of a K=8 MMA 512 B apart (SBO)
+      const uint64_t adesc0 = make_smem_desc(0, 1024, 512, kSwizzle128BBase32B);
       // B: K-major, no swizzle: 8x16B core matrices; K chunks 128 B apart (LBO), 8-row groups 256 B apart (SBO)
       const uint64_t bdesc0 = make_smem_desc(0, 128, 256, kSwizzleNone);
       int32_t wl = 0;
@@ -224,6 +225,8 @@ spmm_tc_kernel(PlanView pv, const float* __restrict__ x, int64_t ldx, const floa
         }
         umma_commit(&empty[s]);
       }
+      // the last commit must land in this CTA's shared memory before the CTA may retire
+      if (n_stages > 0) mbar_wait(&empty[(n_stages - 1) % C::kStages], ((n_stages - 1) / C::kStages) & 1);
     }
   } else if (warp == kMetaWarp) {
     // ===================================== meta loader (TMA) ============================
@@ -327,7 +330,7 @@ spmm_tc_kernel(PlanView pv, const float* __restrict__ x, int64_t ldx, const floa
             if (item < items) {
               const int r = nvec_shift >= 0 ? item >> nvec_shift : item / nvec;
               const int v = item - r * nvec;
-              *reinterpret_cast<float4*>(a_tile + (v >> 3) * 1024 + sw128_offset(r, v & 7)) = tf32_rna4(val[u]);
+              *reinterpret_cast<float4*>(a_tile + (v >> 3) * 1024 + sw128_base32_offset(r, v & 7)) = tf32_rna4(val[u]);
             }
           }
         }

@@ -9,7 +9,7 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 
-SW_NONE, SW_128B, SW_32B = 0, 2, 6
+SW_NONE, SW_128B_BASE32B, SW_128B, SW_32B = 0, 1, 2, 6
 
 
 def smem_desc(lbo, sbo, swizzle):
@@ -24,12 +24,18 @@ def sw128(row, chunk16):
     return row * 128 + ((chunk16 ^ (row & 7)) << 4)
 
 
-def image_mn_major_sw128(At):
-    """At[f, k]: f = M index (128), k = K index (8).  32-feature atoms of 8 rows x 128 B, 1024 B apart."""
+def sw128_base32(row, chunk16):
+    """128-byte rows, 32-byte swizzle granule (Swizzle<2,5,2>): the only MN-major layout tf32 operands have."""
+    return row * 128 + ((chunk16 ^ ((row & 3) << 1)) << 4)
+
+
+def image_mn_major_sw128(At, lbo=1024, sbo=512):
+    """At[f, k]: f = M index (128), k = K index (8).  Atoms of 32 features x 4 k-rows (4 x 128 B):
+    feature blocks `lbo` bytes apart, the two k-halves `sbo` bytes apart."""
     img = np.zeros(4096 // 4, dtype=np.float32)
     for f in range(At.shape[0]):
         for k in range(8):
-            off = (f // 32) * 1024 + sw128(k, (f % 32) // 4) + (f % 4) * 4
+            off = (f // 32) * lbo + (k // 4) * sbo + sw128_base32(k % 4, (f % 32) // 4) + (f % 4) * 4
             img[off // 4] = At[f, k]
     return img
 
@@ -76,27 +82,33 @@ def capi():
 
 
 def test_spmm_layout_mn_major_a_kmajor_b(capi):
-    """The SpMM configuration: A = gathered feature rows (MN-major, 128B swizzle, LBO=1024),
+    """The SpMM configuration: A = gathered feature rows (MN-major, 128B rows with 32B swizzle granule
+    -- SWIZZLE_128B_BASE32B, the only MN-major layout for tf32 -- feature blocks LBO=1024, k-halves SBO=512),
     B = 16x8 sparse tile (K-major, no swizzle, LBO=128 between K chunks, SBO=256 between 8-row groups)."""
     rng = np.random.default_rng(0)
     At = rng.integers(-8, 9, size=(128, 8)).astype(np.float32)
     B = rng.integers(-4, 5, size=(16, 8)).astype(np.float32)
     want = At @ B.T
     got = capi.debug_umma(image_mn_major_sw128(At), image_b_kmajor_noswizzle(B, 128, 256),
-                          smem_desc(1024, 1024, SW_128B), smem_desc(128, 256, SW_NONE),
+                          smem_desc(1024, 512, SW_128B_BASE32B), smem_desc(128, 256, SW_NONE),
                           idesc_tf32(128, 16, True, False), 1, 0, 0)
     err = float(np.abs(got - want).max())
     _report("spmm_layout(A MN-major SW128, B K-major none LBO128/SBO256)", err == 0.0, err)
     if err != 0.0:
         # diagnostics for the next iteration: try the alternative encodings and dump what came back
         alt = capi.debug_umma(image_mn_major_sw128(At), image_b_kmajor_noswizzle(B, 128, 256),
-                              smem_desc(1024, 1024, SW_128B), smem_desc(256, 128, SW_NONE),
+                              smem_desc(1024, 512, SW_128B_BASE32B), smem_desc(256, 128, SW_NONE),
                               idesc_tf32(128, 16, True, False), 1, 0, 0)
         _report("  alt B desc LBO256/SBO128", bool(np.array_equal(alt, want)), float(np.abs(alt - want).max()))
         alt = capi.debug_umma(image_mn_major_sw128(At), image_b_kmajor_sw32(B),
-                              smem_desc(1024, 1024, SW_128B), smem_desc(16, 256, SW_32B),
+                              smem_desc(1024, 512, SW_128B_BASE32B), smem_desc(16, 256, SW_32B),
                               idesc_tf32(128, 16, True, False), 1, 0, 0)
         _report("  alt B SW32", bool(np.array_equal(alt, want)), float(np.abs(alt - want).max()))
+        alt = capi.debug_umma(image_mn_major_sw128(At, 512, 2048), image_b_kmajor_noswizzle(B, 128, 256),
+                              smem_desc(512, 2048, SW_128B_BASE32B), smem_desc(128, 256, SW_NONE),
+                              idesc_tf32(128, 16, True, False), 1, 0, 0)
+        _report("  alt A layout LBO512/SBO2048", bool(np.array_equal(alt, want)), float(np.abs(alt - want).max()))
+        np.save("gpurun_out/umma_probe_spmm_alt_got.npy", alt)
         np.save("gpurun_out/umma_probe_spmm_got.npy", got)
         np.save("gpurun_out/umma_probe_spmm_want.npy", want)
     assert err == 0.0
@@ -111,7 +123,7 @@ def test_spmm_layout_identity_maps_lanes(capi):
     B[3, 0] = 1.0
     B[9, 5] = 1.0
     got = capi.debug_umma(image_mn_major_sw128(At), image_b_kmajor_noswizzle(B, 128, 256),
-                          smem_desc(1024, 1024, SW_128B), smem_desc(128, 256, SW_NONE),
+                          smem_desc(1024, 512, SW_128B_BASE32B), smem_desc(128, 256, SW_NONE),
                           idesc_tf32(128, 16, True, False), 1, 0, 0)
     want = At @ B.T
     ok = np.array_equal(got, want)
@@ -150,12 +162,12 @@ def test_tf32_operand_handling_is_exact_after_rna(capi):
     for n in range(8):
         B[n, n] = 1.0
     got = capi.debug_umma(image_mn_major_sw128(At), image_b_kmajor_noswizzle(B, 128, 256),
-                          smem_desc(1024, 1024, SW_128B), smem_desc(128, 256, SW_NONE),
+                          smem_desc(1024, 512, SW_128B_BASE32B), smem_desc(128, 256, SW_NONE),
                           idesc_tf32(128, 16, True, False), 1, 0, 0)
     assert np.array_equal(got[:, :8], At)
     raw = rng.standard_normal((128, 8)).astype(np.float32)
     got = capi.debug_umma(image_mn_major_sw128(raw), image_b_kmajor_noswizzle(B, 128, 256),
-                          smem_desc(1024, 1024, SW_128B), smem_desc(128, 256, SW_NONE),
+                          smem_desc(1024, 512, SW_128B_BASE32B), smem_desc(128, 256, SW_NONE),
                           idesc_tf32(128, 16, True, False), 1, 0, 0)
     trunc = (raw.view(np.uint32) & np.uint32(0xFFFFE000)).view(np.float32)
     mode = "truncate" if np.array_equal(got[:, :8], trunc) else ("rna" if np.array_equal(got[:, :8], orc.tf32_rna(raw)) else "other")
