@@ -65,6 +65,13 @@ int tcgnn_sgt_cuda(const int32_t* row_ptr, const int32_t* col_idx, int32_t num_n
                    int32_t blk_h, int32_t blk_w, int32_t* block_partition, int32_t* edge_to_col,
                    int32_t* edge_to_row, int64_t* tc_blocks_out, void* stream);
 
+/* Row-panel variant (1-D destination-row sharding): row_ptr describes `num_rows` consecutive rows
+ * (rebased to start at 0) whose col_idx are global node ids in [0, num_cols).  The SGT of a panel
+ * that starts on a window boundary equals the panel's slice of the whole graph's SGT. */
+int tcgnn_sgt_cuda_panel(const int32_t* row_ptr, const int32_t* col_idx, int32_t num_rows, int32_t num_cols,
+                         int64_t num_edges, int32_t blk_h, int32_t blk_w, int32_t* block_partition,
+                         int32_t* edge_to_col, int32_t* edge_to_row, int64_t* tc_blocks_out, void* stream);
+
 /* Plan ---------------------------------------------------------------------------------------
  * Derives the kernel-side tile stream from the caller's SGT arrays (all device pointers, the
  * same five arrays the reference kernels take, TCGNN_kernel.cu:336-346).  One 64-byte record
@@ -73,6 +80,17 @@ int tcgnn_sgt_cuda(const int32_t* row_ptr, const int32_t* col_idx, int32_t num_n
 int tcgnn_plan_create(const int32_t* row_ptr, const int32_t* col_idx, const int32_t* block_partition,
                       const int32_t* edge_to_col, const int32_t* edge_to_row, int32_t num_nodes,
                       int64_t num_edges, int32_t num_windows, void* stream, tcgnn_plan** plan_out);
+/* Row-panel variant for 1-D destination-row sharding (new; the reference is single-GPU): the plan
+ * covers `num_rows` consecutive rows of a graph with `num_cols` nodes.  row_ptr is the panel's own
+ * CSR pointer rebased to start at 0, the SGT arrays are the panel's slices of the global ones
+ * (edge_to_row rebased to the panel), col_idx keeps GLOBAL node ids in [0, num_cols).  X passed to
+ * the kernels has num_cols rows; SpMM writes the panel's num_rows output rows; SDDMM reads the
+ * panel's own feature rows at X[row_base + r].  tcgnn_plan_create == panel with num_cols ==
+ * num_rows and row_base == 0. */
+int tcgnn_plan_create_panel(const int32_t* row_ptr, const int32_t* col_idx, const int32_t* block_partition,
+                            const int32_t* edge_to_col, const int32_t* edge_to_row, int32_t num_rows,
+                            int32_t num_cols, int32_t row_base, int64_t num_edges, int32_t num_windows,
+                            void* stream, tcgnn_plan** plan_out);
 int tcgnn_plan_destroy(tcgnn_plan* plan);
 /* info[0]=num_nodes info[1]=num_edges info[2]=num_windows info[3]=num_tiles info[4]=plan bytes
  * info[5]=distinct (row,col) pairs info[6]=device ordinal info[7]=SM count */

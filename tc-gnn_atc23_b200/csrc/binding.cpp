@@ -62,6 +62,8 @@ struct TensorKey {
 struct PlanEntry {
   std::vector<TensorKey> keys;   // nodePointer, edgeList, blockPartition, edgeToColumn, edgeToRow
   int device = 0;
+  int64_t num_cols = 0;
+  int64_t row_base = 0;
   tcgnn_plan* plan = nullptr;
   std::vector<torch::Tensor> keep;   // nothing kept by default (inputs are borrowed, never retained)
 };
@@ -72,7 +74,8 @@ constexpr size_t kCacheCapacity = 8;
 
 tcgnn_plan* get_plan(const torch::Tensor& nodePointer, const torch::Tensor& edgeList,
                      const torch::Tensor& blockPartition, const torch::Tensor& edgeToColumn,
-                     const torch::Tensor& edgeToRow) {
+                     const torch::Tensor& edgeToRow, int64_t num_cols = -1, int64_t row_base = 0) {
+  if (num_cols < 0) num_cols = nodePointer.size(0) - 1;
   const torch::Tensor* ts[5] = {&nodePointer, &edgeList, &blockPartition, &edgeToColumn, &edgeToRow};
   const int device = nodePointer.get_device();
   std::lock_guard<std::mutex> lock(g_cache_mu);
@@ -84,7 +87,7 @@ tcgnn_plan* get_plan(const torch::Tensor& nodePointer, const torch::Tensor& edge
       it = g_cache.erase(it);
       continue;
     }
-    bool hit = it->device == device;
+    bool hit = it->device == device && it->num_cols == num_cols && it->row_base == row_base;
     for (int i = 0; hit && i < 5; ++i) hit = it->keys[i].matches(*ts[i]);
     if (hit) {
       g_cache.splice(g_cache.begin(), g_cache, it);
@@ -103,10 +106,15 @@ tcgnn_plan* get_plan(const torch::Tensor& nodePointer, const torch::Tensor& edge
   PlanEntry entry;
   for (int i = 0; i < 5; ++i) entry.keys.emplace_back(*ts[i]);
   entry.device = device;
+  entry.num_cols = num_cols;
+  entry.row_base = row_base;
+  TORCH_CHECK(num_cols <= INT32_MAX && row_base >= 0 && row_base + num_nodes <= num_cols,
+              "row panel [", row_base, ", ", row_base + num_nodes, ") does not fit a graph of ", num_cols, " nodes");
   auto stream = c10::cuda::getCurrentCUDAStream(device).stream();
-  const int status = tcgnn_plan_create(
+  const int status = tcgnn_plan_create_panel(
       nodePointer.data_ptr<int32_t>(), edgeList.data_ptr<int32_t>(), blockPartition.data_ptr<int32_t>(),
-      edgeToColumn.data_ptr<int32_t>(), edgeToRow.data_ptr<int32_t>(), static_cast<int32_t>(num_nodes), num_edges,
+      edgeToColumn.data_ptr<int32_t>(), edgeToRow.data_ptr<int32_t>(), static_cast<int32_t>(num_nodes),
+      static_cast<int32_t>(num_cols), static_cast<int32_t>(row_base), num_edges,
       static_cast<int32_t>(blockPartition.size(0)), stream, &entry.plan);
   check_status(status, "tcgnn_plan_create");
   g_cache.push_front(std::move(entry));
@@ -125,7 +133,7 @@ void clear_plan_cache() {
 
 void check_graph(const torch::Tensor& input, const torch::Tensor& nodePointer, const torch::Tensor& edgeList,
                  const torch::Tensor& blockPartition, const torch::Tensor& edgeToColumn,
-                 const torch::Tensor& edgeToRow) {
+                 const torch::Tensor& edgeToRow, int64_t row_base = -1 /* >= 0: row panel of a larger graph */) {
   CHECK_INPUT(input);
   CHECK_INPUT(nodePointer);
   CHECK_INPUT(edgeList);
@@ -140,8 +148,13 @@ void check_graph(const torch::Tensor& input, const torch::Tensor& nodePointer, c
   CHECK_I32(edgeToRow);
   TORCH_CHECK(input.dim() == 2, "input must be [num_nodes, dim]");
   TORCH_CHECK(nodePointer.dim() == 1 && edgeList.dim() == 1, "nodePointer / edgeList must be 1-D");
-  TORCH_CHECK(input.size(0) == nodePointer.size(0) - 1, "input has ", input.size(0), " rows but the graph has ",
-              nodePointer.size(0) - 1, " nodes");
+  if (row_base < 0) {
+    TORCH_CHECK(input.size(0) == nodePointer.size(0) - 1, "input has ", input.size(0), " rows but the graph has ",
+                nodePointer.size(0) - 1, " nodes");
+  } else {
+    TORCH_CHECK(row_base + nodePointer.size(0) - 1 <= input.size(0), "row panel [", row_base, ", ",
+                row_base + nodePointer.size(0) - 1, ") exceeds the ", input.size(0), " rows of input");
+  }
   TORCH_CHECK(input.size(1) >= 1, "input must have at least one feature column");
   const auto dev = input.device();
   TORCH_CHECK(nodePointer.device() == dev && edgeList.device() == dev && blockPartition.device() == dev &&
@@ -152,52 +165,87 @@ void check_graph(const torch::Tensor& input, const torch::Tensor& nodePointer, c
 // ---------------------------------------------------------------------------------------------
 // operators (reference: TCGNN.cpp:63-150)
 // ---------------------------------------------------------------------------------------------
-std::vector<torch::Tensor> spmm_forward(torch::Tensor input, torch::Tensor nodePointer, torch::Tensor edgeList,
-                                        torch::Tensor blockPartition, torch::Tensor edgeToColumn,
-                                        torch::Tensor edgeToRow) {
-  check_graph(input, nodePointer, edgeList, blockPartition, edgeToColumn, edgeToRow);
+torch::Tensor run_spmm(const torch::Tensor& input, const torch::Tensor& nodePointer, const torch::Tensor& edgeList,
+                       const torch::Tensor* edgeAttention, const torch::Tensor& blockPartition,
+                       const torch::Tensor& edgeToColumn, const torch::Tensor& edgeToRow, int64_t row_base) {
+  check_graph(input, nodePointer, edgeList, blockPartition, edgeToColumn, edgeToRow, row_base);
+  const float* weights = nullptr;
+  if (edgeAttention != nullptr) {
+    CHECK_INPUT(*edgeAttention);
+    CHECK_F32(*edgeAttention);
+    TORCH_CHECK(edgeAttention->device() == input.device(), "edgeAttention must be on the same device as input");
+    // [n_heads, E]; like the reference kernel (TCGNN_kernel.cu:529) only head 0 is read.
+    TORCH_CHECK(edgeAttention->dim() >= 1 && edgeAttention->size(-1) == edgeList.size(0),
+                "edgeAttention must be [n_heads, num_edges]");
+    weights = edgeAttention->data_ptr<float>();
+  }
   c10::cuda::CUDAGuard guard(input.device());
-  tcgnn_plan* plan = get_plan(nodePointer, edgeList, blockPartition, edgeToColumn, edgeToRow);
-  auto output = torch::empty_like(input);
+  tcgnn_plan* plan = get_plan(nodePointer, edgeList, blockPartition, edgeToColumn, edgeToRow,
+                              row_base < 0 ? -1 : input.size(0), row_base < 0 ? 0 : row_base);
+  auto output = torch::empty({nodePointer.size(0) - 1, input.size(1)}, input.options());
   auto stream = c10::cuda::getCurrentCUDAStream(input.get_device()).stream();
-  check_status(tcgnn_spmm_f32(plan, input.data_ptr<float>(), input.size(1), nullptr, output.data_ptr<float>(),
+  check_status(tcgnn_spmm_f32(plan, input.data_ptr<float>(), input.size(1), weights, output.data_ptr<float>(),
                               output.size(1), static_cast<int32_t>(input.size(1)), stream),
                "tcgnn_spmm_f32");
-  return {output};
+  return output;
 }
 
-std::vector<torch::Tensor> spmm_forward_AGNN(torch::Tensor input, torch::Tensor nodePointer, torch::Tensor edgeList,
-                                             torch::Tensor edgeAttention, torch::Tensor blockPartition,
-                                             torch::Tensor edgeToColumn, torch::Tensor edgeToRow) {
-  check_graph(input, nodePointer, edgeList, blockPartition, edgeToColumn, edgeToRow);
-  CHECK_INPUT(edgeAttention);
-  CHECK_F32(edgeAttention);
-  TORCH_CHECK(edgeAttention.device() == input.device(), "edgeAttention must be on the same device as input");
-  // [n_heads, E]; like the reference kernel (TCGNN_kernel.cu:529) only head 0 is read.
-  TORCH_CHECK(edgeAttention.dim() >= 1 && edgeAttention.size(-1) == edgeList.size(0),
-              "edgeAttention must be [n_heads, num_edges]");
+torch::Tensor run_sddmm(const torch::Tensor& input, const torch::Tensor& nodePointer, const torch::Tensor& edgeList,
+                        const torch::Tensor& blockPartition, const torch::Tensor& edgeToColumn,
+                        const torch::Tensor& edgeToRow, int64_t row_base) {
+  check_graph(input, nodePointer, edgeList, blockPartition, edgeToColumn, edgeToRow, row_base);
   c10::cuda::CUDAGuard guard(input.device());
-  tcgnn_plan* plan = get_plan(nodePointer, edgeList, blockPartition, edgeToColumn, edgeToRow);
-  auto output = torch::empty_like(input);
-  auto stream = c10::cuda::getCurrentCUDAStream(input.get_device()).stream();
-  check_status(tcgnn_spmm_f32(plan, input.data_ptr<float>(), input.size(1), edgeAttention.data_ptr<float>(),
-                              output.data_ptr<float>(), output.size(1), static_cast<int32_t>(input.size(1)), stream),
-               "tcgnn_spmm_f32 (weighted)");
-  return {output};
-}
-
-std::vector<torch::Tensor> sddmm_forward(torch::Tensor input, torch::Tensor nodePointer, torch::Tensor edgeList,
-                                         torch::Tensor blockPartition, torch::Tensor edgeToColumn,
-                                         torch::Tensor edgeToRow) {
-  check_graph(input, nodePointer, edgeList, blockPartition, edgeToColumn, edgeToRow);
-  c10::cuda::CUDAGuard guard(input.device());
-  tcgnn_plan* plan = get_plan(nodePointer, edgeList, blockPartition, edgeToColumn, edgeToRow);
+  tcgnn_plan* plan = get_plan(nodePointer, edgeList, blockPartition, edgeToColumn, edgeToRow,
+                              row_base < 0 ? -1 : input.size(0), row_base < 0 ? 0 : row_base);
   auto output = torch::empty({edgeList.size(0)}, input.options());
   auto stream = c10::cuda::getCurrentCUDAStream(input.get_device()).stream();
   check_status(tcgnn_sddmm_f32(plan, input.data_ptr<float>(), input.size(1), output.data_ptr<float>(),
                                static_cast<int32_t>(input.size(1)), stream),
                "tcgnn_sddmm_f32");
-  return {output};
+  return output;
+}
+
+std::vector<torch::Tensor> spmm_forward(torch::Tensor input, torch::Tensor nodePointer, torch::Tensor edgeList,
+                                        torch::Tensor blockPartition, torch::Tensor edgeToColumn,
+                                        torch::Tensor edgeToRow) {
+  return {run_spmm(input, nodePointer, edgeList, nullptr, blockPartition, edgeToColumn, edgeToRow, -1)};
+}
+
+std::vector<torch::Tensor> spmm_forward_AGNN(torch::Tensor input, torch::Tensor nodePointer, torch::Tensor edgeList,
+                                             torch::Tensor edgeAttention, torch::Tensor blockPartition,
+                                             torch::Tensor edgeToColumn, torch::Tensor edgeToRow) {
+  return {run_spmm(input, nodePointer, edgeList, &edgeAttention, blockPartition, edgeToColumn, edgeToRow, -1)};
+}
+
+std::vector<torch::Tensor> sddmm_forward(torch::Tensor input, torch::Tensor nodePointer, torch::Tensor edgeList,
+                                         torch::Tensor blockPartition, torch::Tensor edgeToColumn,
+                                         torch::Tensor edgeToRow) {
+  return {run_sddmm(input, nodePointer, edgeList, blockPartition, edgeToColumn, edgeToRow, -1)};
+}
+
+// Row-panel variants for 1-D destination-row sharding (new; the reference is single-GPU): `input` is the
+// all-gathered feature matrix of the whole graph, the five graph tensors describe the caller's row panel
+// (tcgnn_plan_create_panel), `row_base` is the global id of the panel's first row.
+std::vector<torch::Tensor> panel_forward(torch::Tensor input, int64_t row_base, torch::Tensor nodePointer,
+                                         torch::Tensor edgeList, torch::Tensor blockPartition,
+                                         torch::Tensor edgeToColumn, torch::Tensor edgeToRow) {
+  TORCH_CHECK(row_base >= 0, "row_base must be >= 0");
+  return {run_spmm(input, nodePointer, edgeList, nullptr, blockPartition, edgeToColumn, edgeToRow, row_base)};
+}
+
+std::vector<torch::Tensor> panel_forward_AGNN(torch::Tensor input, int64_t row_base, torch::Tensor nodePointer,
+                                              torch::Tensor edgeList, torch::Tensor edgeAttention,
+                                              torch::Tensor blockPartition, torch::Tensor edgeToColumn,
+                                              torch::Tensor edgeToRow) {
+  TORCH_CHECK(row_base >= 0, "row_base must be >= 0");
+  return {run_spmm(input, nodePointer, edgeList, &edgeAttention, blockPartition, edgeToColumn, edgeToRow, row_base)};
+}
+
+std::vector<torch::Tensor> panel_forward_ef(torch::Tensor input, int64_t row_base, torch::Tensor nodePointer,
+                                            torch::Tensor edgeList, torch::Tensor blockPartition,
+                                            torch::Tensor edgeToColumn, torch::Tensor edgeToRow) {
+  TORCH_CHECK(row_base >= 0, "row_base must be >= 0");
+  return {run_sddmm(input, nodePointer, edgeList, blockPartition, edgeToColumn, edgeToRow, row_base)};
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -231,14 +279,17 @@ void check_sgt_args(const torch::Tensor& edgeList, const torch::Tensor& nodePoin
 
 void preprocess_impl(torch::Tensor edgeList, torch::Tensor nodePointer, int64_t num_nodes, int64_t blockSize_h,
                      int64_t blockSize_w, torch::Tensor blockPartition, torch::Tensor edgeToColumn,
-                     torch::Tensor edgeToRow) {
+                     torch::Tensor edgeToRow, int64_t num_cols = -1, bool quiet = false) {
+  if (num_cols < 0) num_cols = num_nodes;
+  TORCH_CHECK(num_cols <= INT32_MAX, "num_cols out of range");
   check_sgt_args(edgeList, nodePointer, num_nodes, blockSize_h, blockSize_w, blockPartition, edgeToColumn, edgeToRow);
   int64_t tc_blocks = 0;
   if (edgeList.is_cuda()) {
     c10::cuda::CUDAGuard guard(edgeList.device());
     auto stream = c10::cuda::getCurrentCUDAStream(edgeList.get_device()).stream();
-    check_status(tcgnn_sgt_cuda(nodePointer.data_ptr<int32_t>(), edgeList.data_ptr<int32_t>(),
-                                static_cast<int32_t>(num_nodes), edgeList.numel(), static_cast<int32_t>(blockSize_h),
+    check_status(tcgnn_sgt_cuda_panel(nodePointer.data_ptr<int32_t>(), edgeList.data_ptr<int32_t>(),
+                                static_cast<int32_t>(num_nodes), static_cast<int32_t>(num_cols), edgeList.numel(),
+                                static_cast<int32_t>(blockSize_h),
                                 static_cast<int32_t>(blockSize_w), blockPartition.data_ptr<int32_t>(),
                                 edgeToColumn.data_ptr<int32_t>(), edgeToRow.data_ptr<int32_t>(), &tc_blocks, stream),
                  "tcgnn_sgt_cuda");
@@ -253,6 +304,7 @@ void preprocess_impl(torch::Tensor edgeList, torch::Tensor nodePointer, int64_t 
     }
     check_status(status, "tcgnn_sgt_cpu");
   }
+  if (quiet) return;
   // same two lines the reference prints (TCGNN.cpp:225) so 1_log2csv.py-style log scraping keeps working
   printf("TC_Blocks:\t%lld\nExp_Edges:\t%lld\n", static_cast<long long>(tc_blocks),
          static_cast<long long>(tc_blocks * blockSize_h * blockSize_w));
@@ -274,6 +326,14 @@ void preprocess_gpu(torch::Tensor edgeList, torch::Tensor nodePointer, int64_t n
   CHECK_CUDA(edgeToColumn);
   CHECK_CUDA(edgeToRow);
   preprocess_impl(edgeList, nodePointer, num_nodes, blockSize_h, blockSize_w, blockPartition, edgeToColumn, edgeToRow);
+}
+
+// SGT of a row panel (sharding): num_rows rows whose column ids are global, in [0, num_cols).  Silent.
+void preprocess_panel(torch::Tensor edgeList, torch::Tensor nodePointer, int64_t num_rows, int64_t num_cols,
+                      int64_t blockSize_h, int64_t blockSize_w, torch::Tensor blockPartition,
+                      torch::Tensor edgeToColumn, torch::Tensor edgeToRow) {
+  preprocess_impl(edgeList, nodePointer, num_rows, blockSize_h, blockSize_w, blockPartition, edgeToColumn, edgeToRow,
+                  num_cols, true);
 }
 
 std::vector<int64_t> plan_info(torch::Tensor nodePointer, torch::Tensor edgeList, torch::Tensor blockPartition,
@@ -300,6 +360,12 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("backward", &spmm_forward, "TC-GNN SPMM backward (CUDA)");
   m.def("backward_ef", &sddmm_forward, "TC-GNN SDDMM backward_ef (CUDA)");
   // additions
+  m.def("preprocess_panel", &preprocess_panel,
+        "SGT of a row panel: (edgeList, nodePointer, num_rows, num_cols, blk_h, blk_w, bp, e2c, e2r)");
+  m.def("panel_forward", &panel_forward, "SpMM of a row panel: (X_all, row_base, nodePointer, edgeList, bp, e2c, e2r)");
+  m.def("panel_forward_AGNN", &panel_forward_AGNN,
+        "weighted SpMM of a row panel: (X_all, row_base, nodePointer, edgeList, edgeAttention, bp, e2c, e2r)");
+  m.def("panel_forward_ef", &panel_forward_ef, "SDDMM of a row panel: (X_all, row_base, nodePointer, edgeList, bp, e2c, e2r)");
   m.def("clear_plan_cache", &clear_plan_cache, "Destroy all cached kernel plans");
   m.def("plan_info", &plan_info, "[num_nodes, num_edges, num_windows, num_tiles, plan_bytes, pairs, device, sms]");
   m.def("launch_count", [](bool reset) { return tcgnn_launch_count(reset ? 1 : 0); }, pybind11::arg("reset") = false,

@@ -56,38 +56,55 @@ int tcgnn_sgt_cpu(const int32_t* row_ptr, const int32_t* col_idx, int32_t num_no
                  tc_blocks_out, num_threads);
 }
 
-int tcgnn_sgt_cuda(const int32_t* row_ptr, const int32_t* col_idx, int32_t num_nodes, int64_t num_edges,
-                   int32_t blk_h, int32_t blk_w, int32_t* block_partition, int32_t* edge_to_col,
-                   int32_t* edge_to_row, int64_t* tc_blocks_out, void* stream) {
-  if (row_ptr == nullptr || block_partition == nullptr || num_nodes < 0 || num_edges < 0 || blk_h <= 0 ||
-      blk_w <= 0 || (num_edges > 0 && (col_idx == nullptr || edge_to_col == nullptr || edge_to_row == nullptr))) {
+int tcgnn_sgt_cuda_panel(const int32_t* row_ptr, const int32_t* col_idx, int32_t num_rows, int32_t num_cols,
+                         int64_t num_edges, int32_t blk_h, int32_t blk_w, int32_t* block_partition,
+                         int32_t* edge_to_col, int32_t* edge_to_row, int64_t* tc_blocks_out, void* stream) {
+  if (row_ptr == nullptr || block_partition == nullptr || num_rows < 0 || num_cols < 0 || num_edges < 0 ||
+      blk_h <= 0 || blk_w <= 0 ||
+      (num_edges > 0 && (col_idx == nullptr || edge_to_col == nullptr || edge_to_row == nullptr))) {
     set_last_error("tcgnn_sgt_cuda: bad argument");
     return TCGNN_ERR_INVALID_ARG;
   }
-  return sgt_cuda(row_ptr, col_idx, num_nodes, num_edges, blk_h, blk_w, block_partition, edge_to_col, edge_to_row,
-                  tc_blocks_out, static_cast<cudaStream_t>(stream));
+  return sgt_cuda(row_ptr, col_idx, num_rows, num_cols, num_edges, blk_h, blk_w, block_partition, edge_to_col,
+                  edge_to_row, tc_blocks_out, static_cast<cudaStream_t>(stream));
 }
 
-int tcgnn_plan_create(const int32_t* row_ptr, const int32_t* col_idx, const int32_t* block_partition,
-                      const int32_t* edge_to_col, const int32_t* edge_to_row, int32_t num_nodes, int64_t num_edges,
-                      int32_t num_windows, void* stream, tcgnn_plan** plan_out) {
+int tcgnn_sgt_cuda(const int32_t* row_ptr, const int32_t* col_idx, int32_t num_nodes, int64_t num_edges,
+                   int32_t blk_h, int32_t blk_w, int32_t* block_partition, int32_t* edge_to_col,
+                   int32_t* edge_to_row, int64_t* tc_blocks_out, void* stream) {
+  return tcgnn_sgt_cuda_panel(row_ptr, col_idx, num_nodes, num_nodes, num_edges, blk_h, blk_w, block_partition,
+                              edge_to_col, edge_to_row, tc_blocks_out, stream);
+}
+
+int tcgnn_plan_create_panel(const int32_t* row_ptr, const int32_t* col_idx, const int32_t* block_partition,
+                            const int32_t* edge_to_col, const int32_t* edge_to_row, int32_t num_rows, int32_t num_cols,
+                            int32_t row_base, int64_t num_edges, int32_t num_windows, void* stream,
+                            tcgnn_plan** plan_out) {
   if (plan_out == nullptr) {
     set_last_error("tcgnn_plan_create: plan_out is null");
     return TCGNN_ERR_INVALID_ARG;
   }
   *plan_out = nullptr;
-  const int64_t expect_windows = (static_cast<int64_t>(num_nodes) + TCGNN_BLK_H - 1) / TCGNN_BLK_H;
-  if (row_ptr == nullptr || block_partition == nullptr || num_nodes <= 0 || num_edges < 0 ||
-      num_edges > 0x7FFFFFFFLL || num_windows != expect_windows ||
+  const int64_t expect_windows = (static_cast<int64_t>(num_rows) + TCGNN_BLK_H - 1) / TCGNN_BLK_H;
+  if (row_ptr == nullptr || block_partition == nullptr || num_rows <= 0 || num_edges < 0 ||
+      num_edges > 0x7FFFFFFFLL || num_windows != expect_windows || row_base < 0 ||
+      static_cast<int64_t>(row_base) + num_rows > num_cols ||
       (num_edges > 0 && (col_idx == nullptr || edge_to_col == nullptr || edge_to_row == nullptr))) {
-    set_last_error("tcgnn_plan_create: bad argument (num_nodes=%d num_edges=%lld num_windows=%d, expected %lld "
-                   "windows of %d rows)",
-                   num_nodes, static_cast<long long>(num_edges), num_windows, static_cast<long long>(expect_windows),
-                   TCGNN_BLK_H);
+    set_last_error("tcgnn_plan_create: bad argument (num_rows=%d num_cols=%d row_base=%d num_edges=%lld "
+                   "num_windows=%d, expected %lld windows of %d rows)",
+                   num_rows, num_cols, row_base, static_cast<long long>(num_edges), num_windows,
+                   static_cast<long long>(expect_windows), TCGNN_BLK_H);
     return TCGNN_ERR_INVALID_ARG;
   }
-  return plan_create(row_ptr, col_idx, block_partition, edge_to_col, edge_to_row, num_nodes, num_edges, num_windows,
-                     static_cast<cudaStream_t>(stream), plan_out);
+  return plan_create(row_ptr, col_idx, block_partition, edge_to_col, edge_to_row, num_rows, num_cols, row_base,
+                     num_edges, num_windows, static_cast<cudaStream_t>(stream), plan_out);
+}
+
+int tcgnn_plan_create(const int32_t* row_ptr, const int32_t* col_idx, const int32_t* block_partition,
+                      const int32_t* edge_to_col, const int32_t* edge_to_row, int32_t num_nodes, int64_t num_edges,
+                      int32_t num_windows, void* stream, tcgnn_plan** plan_out) {
+  return tcgnn_plan_create_panel(row_ptr, col_idx, block_partition, edge_to_col, edge_to_row, num_nodes, num_nodes, 0,
+                                 num_edges, num_windows, stream, plan_out);
 }
 
 int tcgnn_plan_destroy(tcgnn_plan* plan) { return plan_destroy(plan); }

@@ -29,7 +29,9 @@ struct PlanView {  // device pointers, passed by value to kernels
   const TileMeta* tiles;        // [num_tiles]
   const int32_t* win_tile_ptr;  // [num_windows + 1] exclusive scan of blockPartition
   const int32_t* eperm;         // [num_pairs] tile order -> CSR edge id (lazy; weighted SpMM / SDDMM)
-  int32_t num_nodes;
+  int32_t num_nodes;            // rows of the plan
+  int32_t num_cols;             // rows of X
+  int32_t row_base;             // global id of row 0 (row panels)
   int32_t num_windows;
   int32_t num_tiles;
   int32_t num_pairs;

@@ -154,13 +154,13 @@ __global__ void init_tiles_kernel(TileMeta* tiles, const int32_t* __restrict__ w
 __global__ void scatter_edges_kernel(TileMeta* tiles, const int32_t* __restrict__ win_tile_ptr,
                                      const int32_t* __restrict__ col_idx, const int32_t* __restrict__ edge_to_col,
                                      const int32_t* __restrict__ edge_to_row, int64_t num_edges, int32_t num_nodes,
-                                     int32_t* bad) {
+                                     int32_t num_cols, int32_t* bad) {
   for (int64_t e = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; e < num_edges;
        e += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const int32_t r = edge_to_row[e];
     const int32_t c = edge_to_col[e];
     const int32_t x = col_idx[e];
-    if (r < 0 || r >= num_nodes || c < 0 || x < 0 || x >= num_nodes) { atomicAdd(bad, 1); continue; }
+    if (r < 0 || r >= num_nodes || c < 0 || x < 0 || x >= num_cols) { atomicAdd(bad, 1); continue; }
     const int32_t w = r / TCGNN_BLK_H;
     const int32_t t0 = win_tile_ptr[w];
     const int32_t g = t0 + c / TCGNN_BLK_W;
@@ -216,8 +216,9 @@ static int grid_for(int64_t n, int threads) {
   } while (0)
 
 int plan_create(const int32_t* row_ptr, const int32_t* col_idx, const int32_t* block_partition,
-                const int32_t* edge_to_col, const int32_t* edge_to_row, int32_t num_nodes, int64_t num_edges,
-                int32_t num_windows, cudaStream_t stream, tcgnn_plan** plan_out) {
+                const int32_t* edge_to_col, const int32_t* edge_to_row, int32_t num_nodes, int32_t num_cols,
+                int32_t row_base, int64_t num_edges, int32_t num_windows, cudaStream_t stream,
+                tcgnn_plan** plan_out) {
   int status = TCGNN_OK;
   tcgnn_plan* p = new (std::nothrow) tcgnn_plan();
   if (p == nullptr) return TCGNN_ERR_OOM;
@@ -230,6 +231,8 @@ int plan_create(const int32_t* row_ptr, const int32_t* col_idx, const int32_t* b
   p->edge_to_col = edge_to_col;
   p->edge_to_row = edge_to_row;
   p->num_nodes = num_nodes;
+  p->num_cols = num_cols;
+  p->row_base = row_base;
   p->num_edges = num_edges;
   p->num_windows = num_windows;
   PLAN_CUDA(cudaGetDevice(&dev));
@@ -275,7 +278,7 @@ int plan_create(const int32_t* row_ptr, const int32_t* col_idx, const int32_t* b
     if (num_edges > 0) {
       scatter_edges_kernel<<<grid_for(num_edges, 256), 256, 0, stream>>>(p->tiles, p->win_tile_ptr, col_idx,
                                                                         edge_to_col, edge_to_row, num_edges,
-                                                                        num_nodes, p->flag);
+                                                                        num_nodes, num_cols, p->flag);
       count_launch();
     }
     PLAN_CUDA(exclusive_scan(LoadTilePopc{p->tiles}, p->num_tiles, tile_ofs, scratch, stream));

@@ -12,7 +12,9 @@ struct tcgnn_plan {
   const int32_t* col_idx = nullptr;
   const int32_t* edge_to_col = nullptr;
   const int32_t* edge_to_row = nullptr;
-  int32_t num_nodes = 0;
+  int32_t num_nodes = 0;   // rows covered by the plan (panel rows)
+  int32_t num_cols = 0;    // rows of X (== num_nodes unless the plan is a row panel of a larger graph)
+  int32_t row_base = 0;    // global id of the plan's row 0
   int64_t num_edges = 0;
   int32_t num_windows = 0;
   int32_t num_tiles = 0;
@@ -36,6 +38,8 @@ struct tcgnn_plan {
     v.win_tile_ptr = win_tile_ptr;
     v.eperm = eperm;
     v.num_nodes = num_nodes;
+    v.num_cols = num_cols;
+    v.row_base = row_base;
     v.num_windows = num_windows;
     v.num_tiles = num_tiles;
     v.num_pairs = num_pairs;
@@ -49,8 +53,9 @@ void set_last_error(const char* fmt, ...);
 void count_launch(int n = 1);
 
 int plan_create(const int32_t* row_ptr, const int32_t* col_idx, const int32_t* block_partition,
-                const int32_t* edge_to_col, const int32_t* edge_to_row, int32_t num_nodes, int64_t num_edges,
-                int32_t num_windows, cudaStream_t stream, tcgnn_plan** plan_out);
+                const int32_t* edge_to_col, const int32_t* edge_to_row, int32_t num_nodes, int32_t num_cols,
+                int32_t row_base, int64_t num_edges, int32_t num_windows, cudaStream_t stream,
+                tcgnn_plan** plan_out);
 int plan_destroy(tcgnn_plan* plan);
 int plan_ensure_eperm(tcgnn_plan* plan, cudaStream_t stream);
 int plan_ensure_scratch(tcgnn_plan* plan, float** slot, size_t count);
@@ -60,7 +65,8 @@ int plan_ensure_groups(tcgnn_plan* plan, cudaStream_t stream);   // synchronises
 int spmm_launch(tcgnn_plan* plan, const float* x, int64_t ldx, const float* edge_weight, float* y, int64_t ldy,
                 int32_t dim, cudaStream_t stream);
 int sddmm_launch(tcgnn_plan* plan, const float* x, int64_t ldx, float* edge_out, int32_t dim, cudaStream_t stream);
-int sgt_cuda(const int32_t* row_ptr, const int32_t* col_idx, int32_t num_nodes, int64_t num_edges, int32_t blk_h,
+int sgt_cuda(const int32_t* row_ptr, const int32_t* col_idx, int32_t num_nodes, int32_t num_cols, int64_t num_edges,
+             int32_t blk_h,
              int32_t blk_w, int32_t* block_partition, int32_t* edge_to_col, int32_t* edge_to_row,
              int64_t* tc_blocks_out, cudaStream_t stream);
 int debug_umma(const void* a_image, int32_t a_bytes, const void* b_image, int32_t b_bytes, uint64_t adesc,

@@ -212,7 +212,7 @@ sddmm_tc_kernel(PlanView pv, const int4* __restrict__ groups, int32_t num_groups
             if ((row >> 3) < ntiles) node = meta[row >> 3].cols[row & 7];
           } else {
             node = win * TCGNN_BLK_H + (row - 128);
-            if (node >= pv.num_nodes) node = -1;
+            node = node < pv.num_nodes ? node + pv.row_base : -1;   // the window's own rows (global ids)
           }
           const int f = f0 + v * 4;
           if (node >= 0 && f < dim) {

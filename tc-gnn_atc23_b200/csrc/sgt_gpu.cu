@@ -119,7 +119,7 @@ sgt_small_windows_kernel(const int32_t* __restrict__ row_ptr, const int32_t* __r
 // Persistent CTAs; CTA b owns bitmap/prefix slices [b * words, (b+1) * words).
 __global__ void __launch_bounds__(kLargeThreads)
 sgt_large_windows_kernel(const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ col_idx,
-                         int32_t num_nodes, int32_t blk_h, int32_t blk_w, const int32_t* __restrict__ large_list,
+                         int32_t num_nodes, int32_t num_cols, int32_t blk_h, int32_t blk_w, const int32_t* __restrict__ large_list,
                          const int32_t* __restrict__ large_count, uint32_t* __restrict__ bitmaps,
                          uint32_t* __restrict__ prefixes, int32_t words, int32_t* __restrict__ block_partition,
                          int32_t* __restrict__ edge_to_col, unsigned long long* __restrict__ total_blocks,
@@ -139,7 +139,7 @@ sgt_large_windows_kernel(const int32_t* __restrict__ row_ptr, const int32_t* __r
     __syncthreads();
     for (int32_t e = s + tid; e < t; e += kLargeThreads) {
       const uint32_t c = static_cast<uint32_t>(col_idx[e]);
-      if (c >= static_cast<uint32_t>(num_nodes)) { atomicAdd(bad, 1); continue; }
+      if (c >= static_cast<uint32_t>(num_cols)) { atomicAdd(bad, 1); continue; }
       atomicOr(&bits[c >> 5], 1u << (c & 31));
     }
     if (tid == 0) carry_s = 0;
@@ -170,7 +170,7 @@ sgt_large_windows_kernel(const int32_t* __restrict__ row_ptr, const int32_t* __r
     }
     for (int32_t e = s + tid; e < t; e += kLargeThreads) {
       const uint32_t c = static_cast<uint32_t>(col_idx[e]);
-      if (c >= static_cast<uint32_t>(num_nodes)) continue;
+      if (c >= static_cast<uint32_t>(num_cols)) continue;
       edge_to_col[e] = static_cast<int32_t>(pre[c >> 5] + __popc(bits[c >> 5] & ((1u << (c & 31)) - 1u)));
     }
     __syncthreads();
@@ -179,7 +179,8 @@ sgt_large_windows_kernel(const int32_t* __restrict__ row_ptr, const int32_t* __r
 
 }  // namespace
 
-int sgt_cuda(const int32_t* row_ptr, const int32_t* col_idx, int32_t num_nodes, int64_t num_edges, int32_t blk_h,
+int sgt_cuda(const int32_t* row_ptr, const int32_t* col_idx, int32_t num_nodes, int32_t num_cols, int64_t num_edges,
+             int32_t blk_h,
              int32_t blk_w, int32_t* block_partition, int32_t* edge_to_col, int32_t* edge_to_row,
              int64_t* tc_blocks_out, cudaStream_t stream) {
   const int64_t num_windows64 = (static_cast<int64_t>(num_nodes) + blk_h - 1) / blk_h;
@@ -195,7 +196,7 @@ int sgt_cuda(const int32_t* row_ptr, const int32_t* col_idx, int32_t num_nodes, 
   uint32_t* bitmaps = nullptr;
   int32_t host_counts[2] = {0, 0};
   unsigned long long host_total = 0;
-  const int32_t words = (num_nodes + 31) / 32;
+  const int32_t words = (num_cols + 31) / 32;   // hub-window bitmap spans the column id range
   int sms = 148;
   int dev = 0;
   if ((e = cudaGetDevice(&dev)) != cudaSuccess) goto done;
@@ -226,7 +227,7 @@ int sgt_cuda(const int32_t* row_ptr, const int32_t* col_idx, int32_t num_nodes, 
     int grid = host_counts[0] < sms * 2 ? host_counts[0] : sms * 2;
     if ((e = cudaMalloc(&bitmaps, sizeof(uint32_t) * 2 * static_cast<size_t>(grid) * words)) != cudaSuccess) goto done;
     sgt_large_windows_kernel<<<grid, kLargeThreads, 0, stream>>>(
-        row_ptr, col_idx, num_nodes, blk_h, blk_w, large_list, large_list + num_windows, bitmaps,
+        row_ptr, col_idx, num_nodes, num_cols, blk_h, blk_w, large_list, large_list + num_windows, bitmaps,
         bitmaps + static_cast<size_t>(grid) * words, words, block_partition, edge_to_col, total,
         large_list + num_windows + 1);
     count_launch();
@@ -239,7 +240,7 @@ int sgt_cuda(const int32_t* row_ptr, const int32_t* col_idx, int32_t num_nodes, 
     goto done;
   if ((e = cudaStreamSynchronize(stream)) != cudaSuccess) goto done;
   if (host_counts[1] != 0) {
-    set_last_error("tcgnn_sgt_cuda: %d column ids are outside [0, num_nodes)", host_counts[1]);
+    set_last_error("tcgnn_sgt_cuda: %d column ids are outside [0, num_cols)", host_counts[1]);
     status = TCGNN_ERR_INVALID_ARG;
     e = cudaSuccess;
     goto cleanup;

@@ -38,13 +38,15 @@ def lib() -> C.CDLL:
         sgt_args = [vp, vp, i32, i64, i32, i32, vp, vp, vp, C.POINTER(i64)]
         L.tcgnn_sgt_cpu.argtypes = sgt_args + [i32]
         L.tcgnn_sgt_cuda.argtypes = sgt_args + [vp]
+        L.tcgnn_sgt_cuda_panel.argtypes = [vp, vp, i32, i32, i64, i32, i32, vp, vp, vp, C.POINTER(i64), vp]
         L.tcgnn_plan_create.argtypes = [vp, vp, vp, vp, vp, i32, i64, i32, vp, C.POINTER(vp)]
+        L.tcgnn_plan_create_panel.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i64, i32, vp, C.POINTER(vp)]
         L.tcgnn_plan_destroy.argtypes = [vp]
         L.tcgnn_plan_info.argtypes = [vp, C.POINTER(i64)]
         L.tcgnn_spmm_f32.argtypes = [vp, vp, i64, vp, vp, i64, i32, vp]
         L.tcgnn_sddmm_f32.argtypes = [vp, vp, i64, vp, i32, vp]
         L.tcgnn_debug_umma.argtypes = [vp, i32, vp, i32, u64, u64, u32, i32, i32, i32, vp, i32, vp]
-        for name in ("tcgnn_sgt_cpu", "tcgnn_sgt_cuda", "tcgnn_plan_create", "tcgnn_plan_destroy", "tcgnn_plan_info",
+        for name in ("tcgnn_sgt_cpu", "tcgnn_sgt_cuda", "tcgnn_sgt_cuda_panel", "tcgnn_plan_create", "tcgnn_plan_create_panel", "tcgnn_plan_destroy", "tcgnn_plan_info",
                      "tcgnn_spmm_f32", "tcgnn_sddmm_f32", "tcgnn_debug_umma"):
             getattr(L, name).restype = C.c_int
         _lib = L
@@ -91,14 +93,17 @@ def sgt_cuda(row_ptr, col_idx, num_nodes, block_partition, edge_to_col, edge_to_
 class Plan:
     """Owns a tcgnn_plan; keeps the five device tensors alive (the plan borrows their memory)."""
 
-    def __init__(self, row_ptr, col_idx, block_partition, edge_to_col, edge_to_row):
+    def __init__(self, row_ptr, col_idx, block_partition, edge_to_col, edge_to_row, num_cols=None, row_base=0):
         self._tensors = (row_ptr, col_idx, block_partition, edge_to_col, edge_to_row)
         self.num_nodes = row_ptr.numel() - 1
         self.num_edges = col_idx.numel()
+        self.num_cols = self.num_nodes if num_cols is None else num_cols
+        self.row_base = row_base
         self._h = C.c_void_p()
-        check(lib().tcgnn_plan_create(_ptr(row_ptr), _ptr(col_idx), _ptr(block_partition), _ptr(edge_to_col),
-                                      _ptr(edge_to_row), self.num_nodes, self.num_edges, block_partition.numel(),
-                                      _stream(), C.byref(self._h)), "tcgnn_plan_create")
+        check(lib().tcgnn_plan_create_panel(_ptr(row_ptr), _ptr(col_idx), _ptr(block_partition), _ptr(edge_to_col),
+                                            _ptr(edge_to_row), self.num_nodes, self.num_cols, row_base,
+                                            self.num_edges, block_partition.numel(), _stream(), C.byref(self._h)),
+              "tcgnn_plan_create_panel")
 
     def info(self):
         buf = (C.c_int64 * 8)()

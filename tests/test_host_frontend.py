@@ -1,0 +1,63 @@
+"""CPU tests of the host-side mirror of the reference's Python layer: config constants, synthetic
+graph generators, TCGNN_dataset attributes, gnn_conv surface (import only -- compute needs a GPU)."""
+import numpy as np
+import pytest
+import torch
+
+
+def test_config_constants():
+    import config
+    assert (config.BLK_H, config.BLK_W, config.WARP_SIZE) == (16, 8, 32)   # reference config.py:1-3
+    assert config.func(0) == 1 and config.func(5) == 5
+
+
+@pytest.mark.parametrize("kind", ["uniform", "rmat"])
+def test_synthetic_graph_is_reference_format(kind):
+    import graphgen
+    n, target = 4000, 90000
+    rp, ci = graphgen.synthetic_graph(n, target, kind=kind, seed=3)
+    assert rp.dtype == torch.int32 and ci.dtype == torch.int32
+    assert rp.numel() == n + 1 and int(rp[0]) == 0 and int(rp[-1]) == ci.numel()
+    assert 0.99 * target <= ci.numel() <= target
+    rpn, cin = rp.numpy(), ci.numpy()
+    assert (np.diff(rpn) >= 0).all() and cin.min() >= 0 and cin.max() < n
+    for r in (0, 1, n // 2, n - 1):                       # sorted, unique columns per row
+        row = cin[rpn[r]:rpn[r + 1]]
+        assert (np.diff(row) > 0).all()
+    # symmetric adjacency (the reference's backward assumes A == A^T)
+    from scipy.sparse import csr_matrix
+    a = csr_matrix((np.ones(len(cin), np.int8), cin, rpn), shape=(n, n))
+    assert (a != a.T).nnz == 0
+    rp2, ci2 = graphgen.synthetic_graph(n, target, kind=kind, seed=3)
+    assert torch.equal(rp, rp2) and torch.equal(ci, ci2)  # seeded
+
+
+def test_dataset_synthetic_and_npz(tmp_path):
+    from dataset import TCGNN_dataset
+    ds = TCGNN_dataset("uniform:500:6000:1", 16, 7, load_from_txt=False, seed=0)
+    assert ds.num_nodes == 500 and ds.num_features == 16 and ds.num_classes == 7
+    assert ds.row_pointers.dtype == torch.int32 and ds.column_index.dtype == torch.int32
+    assert ds.x.shape == (500, 16) and ds.y.shape == (500,) and int(ds.y.sum()) == 500
+    assert ds.num_edges == ds.column_index.numel()
+    # npz path: same CSR as scipy coo -> csr (reference dataset.py:94-104), duplicates merged
+    src = np.array([0, 0, 1, 2, 2, 2]); dst = np.array([1, 1, 2, 0, 1, 1])
+    f = tmp_path / "g.npz"
+    np.savez(f, src_li=src, dst_li=dst, num_nodes=3)
+    ds2 = TCGNN_dataset(str(f), 4, 2, load_from_txt=False)
+    assert ds2.row_pointers.tolist() == [0, 1, 2, 4]
+    assert ds2.column_index.tolist() == [1, 2, 0, 1]
+    # name of a reference dataset that is not on disk -> the like-named synthetic workload
+    ds3 = TCGNN_dataset("tcgnn-ae-graphs/cora.npz", 16, 7, load_from_txt=False, seed=0)
+    assert ds3.num_nodes == 2708
+
+
+def test_gnn_conv_surface():
+    import gnn_conv
+    for nm in ("TCGNNFunction", "TCGNNFunction_SAG", "TCGNNFunction_GIN", "TCGNNFunction_AGNN", "SAG", "GCNConv",
+               "GINConv", "AGNNConv", "gen_test_tensor"):
+        assert hasattr(gnn_conv, nm)
+    assert gnn_conv.n_heads == 1
+    conv = gnn_conv.AGNNConv(8, 4)
+    assert conv.weights.shape == (8, 4) and conv.attention_w.shape == (1, 1)
+    t = gnn_conv.gen_test_tensor(torch.zeros(5, 3))
+    assert t.tolist() == [[float(i)] * 3 for i in range(5)]
