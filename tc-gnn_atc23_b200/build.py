@@ -28,7 +28,7 @@ CUDA_HOME = os.environ.get("CUDA_HOME", "/usr/local/cuda")
 NVCC = os.path.join(CUDA_HOME, "bin", "nvcc")
 
 LIB_NAME = "libtcgnn_b200.so"
-CU_SOURCES = ["capi.cu", "plan.cu", "spmm_tc.cu", "sddmm_tc.cu", "sgt_gpu.cu", "umma_probe.cu"]
+CU_SOURCES = ["capi.cu", "plan.cu", "round_pack.cu", "spmm_tc.cu", "sddmm_tc.cu", "sgt_gpu.cu", "umma_probe.cu"]
 CPP_SOURCES = ["sgt_cpu.cpp"]
 HEADERS = ["common.cuh", "plan.h", os.path.join(INCLUDE, "tcgnn_b200.h")]
 

@@ -27,6 +27,8 @@ struct tcgnn_plan {
   int32_t* eperm = nullptr;           // [num_pairs]   lazy (weighted SpMM / SDDMM)
   float* weight_perm = nullptr;       // [num_pairs]   lazy: edge weights in tile order
   float* sddmm_perm = nullptr;        // [num_pairs]   lazy: SDDMM results in tile order
+  float* x_round = nullptr;           // lazy, grows: tf32-rounded, 16B-row-aligned copy of the current X
+  size_t x_round_cap = 0;             // floats
   int4* groups = nullptr;             // [num_groups]  lazy: SDDMM work units {tile_start, ntiles, win, 0}
   int32_t num_groups = 0;
   int32_t* flag = nullptr;            // device error counter
@@ -60,6 +62,10 @@ int plan_destroy(tcgnn_plan* plan);
 int plan_ensure_eperm(tcgnn_plan* plan, cudaStream_t stream);
 int plan_ensure_scratch(tcgnn_plan* plan, float** slot, size_t count);
 int plan_ensure_groups(tcgnn_plan* plan, cudaStream_t stream);   // synchronises the stream on first use
+// Xr = cvt.rna.tf32(X[:, :dim]) packed as [num_cols, ldr] (ldr % 4 == 0) into the plan's scratch (round_pack.cu).
+// Ops on one plan must be stream-ordered (they share this scratch).
+int round_pack_launch(tcgnn_plan* plan, const float* x, int64_t ldx, int32_t dim, int64_t ldr, cudaStream_t stream,
+                      const float** xr_out);
 
 // kernels (spmm_tc.cu / sddmm_tc.cu / sgt_gpu.cu / umma_probe.cu)
 int spmm_launch(tcgnn_plan* plan, const float* x, int64_t ldx, const float* edge_weight, float* y, int64_t ldy,

@@ -1,0 +1,84 @@
+// Operand preparation shared by SpMM and SDDMM: Xr = cvt.rna.tf32.f32(X), written once per call
+// into a plan-owned scratch with a 16-byte aligned leading dimension.
+//
+// The reference rounds every operand element with wmma::__float_to_tf32 inside its inner loops
+// (/root/reference TCGNN_conv/TCGNN_kernel.cu:436-444, :560-567, :701-709), i.e. once per USE.
+// tcgen05.mma reads fp32 bit patterns from shared memory and ignores the low 13 mantissa bits
+// (truncation), so feeding it raw X would bias every product.  Rounding once per ELEMENT here gives
+// bit-identical operands to the reference's and lets the gather kernels move rows with cp.async
+// (no register pass).  HBM-bound elementwise pass: 2 * N * D * 4 bytes, grid-stride, 128-bit accesses.
+#include "plan.h"
+
+namespace tcgnn {
+
+namespace {
+
+__global__ void __launch_bounds__(256)
+tf32_round_pack_kernel(const float* __restrict__ x, int64_t ldx, int32_t dim, int64_t rows, float* __restrict__ out,
+                       int64_t ldr, int vec_ok) {
+  const int32_t nvec = static_cast<int32_t>(ldr >> 2);
+  const int64_t total = rows * nvec;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = i / nvec;
+    const int32_t f = static_cast<int32_t>(i - r * nvec) * 4;
+    const float* src = x + r * ldx + f;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (vec_ok && f + 4 <= dim) {
+      v = __ldg(reinterpret_cast<const float4*>(src));
+    } else {
+      if (f + 0 < dim) v.x = __ldg(src + 0);
+      if (f + 1 < dim) v.y = __ldg(src + 1);
+      if (f + 2 < dim) v.z = __ldg(src + 2);
+      if (f + 3 < dim) v.w = __ldg(src + 3);
+    }
+    *reinterpret_cast<float4*>(out + r * ldr + f) = tf32_rna4(v);
+  }
+}
+
+}  // namespace
+
+int round_pack_launch(tcgnn_plan* plan, const float* x, int64_t ldx, int32_t dim, int64_t ldr, cudaStream_t stream,
+                      const float** xr_out) {
+  const int64_t rows = plan->num_cols;
+  const size_t need = static_cast<size_t>(rows) * static_cast<size_t>(ldr);
+  {
+    std::lock_guard<std::mutex> lock(plan->mu);
+    if (plan->x_round_cap < need) {
+      if (plan->x_round != nullptr) {
+        // the old buffer may still be read by kernels queued on `stream`
+        cudaError_t e = cudaStreamSynchronize(stream);
+        if (e == cudaSuccess) e = cudaFree(plan->x_round);
+        plan->x_round = nullptr;
+        plan->x_round_cap = 0;
+        if (e != cudaSuccess) {
+          set_last_error("releasing the tf32 scratch failed: %s", cudaGetErrorString(e));
+          return TCGNN_ERR_CUDA;
+        }
+      }
+      cudaError_t e = cudaMalloc(&plan->x_round, need * sizeof(float));
+      if (e != cudaSuccess) {
+        plan->x_round = nullptr;
+        set_last_error("cudaMalloc(%zu bytes of tf32 scratch) failed: %s", need * sizeof(float), cudaGetErrorString(e));
+        return TCGNN_ERR_OOM;
+      }
+      plan->x_round_cap = need;
+    }
+  }
+  const int vec_ok = (reinterpret_cast<uintptr_t>(x) % 16 == 0) && (ldx % 4 == 0);
+  const int64_t total = rows * (ldr >> 2);
+  int64_t g = (total + 255) / 256;
+  if (g > static_cast<int64_t>(plan->num_sms) * 16) g = static_cast<int64_t>(plan->num_sms) * 16;
+  if (g < 1) g = 1;
+  tf32_round_pack_kernel<<<static_cast<int>(g), 256, 0, stream>>>(x, ldx, dim, rows, plan->x_round, ldr, vec_ok);
+  count_launch();
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_last_error("tf32_round_pack_kernel launch failed: %s", cudaGetErrorString(e));
+    return TCGNN_ERR_CUDA;
+  }
+  *xr_out = plan->x_round;
+  return TCGNN_OK;
+}
+
+}  // namespace tcgnn

@@ -11,9 +11,13 @@
 // written (tile occupancy mask), in tile order; a second pass restores CSR edge order.
 //
 // A pipeline stage is one 32-feature chunk of one group: A 16 KB + B 2 KB + the group's 16 tile
-// records (TMA bulk copy).  CTA = 22 warps:
+// records (TMA bulk copy).  X is first rounded to tf32 (cvt.rna) and packed once per call
+// (round_pack.cu), so the row gathers are plain asynchronous copies.  CTA = 10 warps:
 //   warps 0-3  epilogue     TMEM -> registers -> masked scatter of edge values
-//   warp  4    MMA issuer   warp 5  meta loader (TMA)   warps 6-21  producers (4 groups of 4)
+//   warp  4    MMA issuer   warp 5  meta loader (TMA)
+//   warps 6-9  producers    cp.async (LDGSTS, zero-fill) of 128 gathered rows + the window's 16 rows,
+//                           32 features each, into the 128B-swizzled K-major images; completion
+//                           arrives on the stage's mbarrier (producers run up to kStages ahead)
 #include "plan.h"
 
 namespace tcgnn {
@@ -25,9 +29,8 @@ constexpr int kEpiWarps = 4;
 constexpr int kMmaWarp = 4;
 constexpr int kMetaWarp = 5;
 constexpr int kProducerWarp0 = 6;
-constexpr int kProdGroups = 4;
-constexpr int kProdPerGroup = 4;
-constexpr int kWarps = kProducerWarp0 + kProdGroups * kProdPerGroup;
+constexpr int kProducers = 4;
+constexpr int kWarps = kProducerWarp0 + kProducers;
 constexpr int kThreads = kWarps * 32;
 constexpr int kAcc = 4;
 constexpr int kGroupTiles = 16;
@@ -51,8 +54,9 @@ __device__ __forceinline__ int32_t first_group_at_or_after(const int4* __restric
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
-sddmm_tc_kernel(PlanView pv, const int4* __restrict__ groups, int32_t num_groups, const float* __restrict__ x,
-                int64_t ldx, float* __restrict__ out_perm, int32_t dim, int vec_ok) {
+sddmm_tc_kernel(PlanView pv, const int4* __restrict__ groups, int32_t num_groups,
+                const float* __restrict__ x /* tf32-rounded, 16B aligned */, int64_t ldx /* % 4 == 0 */,
+                float* __restrict__ out_perm, int32_t dim) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* a_smem = smem;
@@ -79,7 +83,7 @@ sddmm_tc_kernel(PlanView pv, const int4* __restrict__ groups, int32_t num_groups
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&meta_full[s], 1);
-      mbar_init(&full[s], kProdPerGroup);
+      mbar_init(&full[s], kProducers * 32);   // every producer thread, on completion of its cp.async copies
       mbar_init(&empty[s], 1);
     }
     for (int b = 0; b < kAcc; ++b) {
@@ -148,6 +152,7 @@ sddmm_tc_kernel(PlanView pv, const int4* __restrict__ groups, int32_t num_groups
           tc_fence_after();
         }
         mbar_wait(&full[s], (k / kStages) & 1);
+        fence_proxy_async_smem();   // cp.async (generic proxy) writes -> tcgen05 operand reads
         tc_fence_after();
         const uint32_t a_addr = smem_u32(a_smem + s * kAStageBytes);
         const uint32_t b_addr = smem_u32(b_smem + s * kBStageBytes);
@@ -184,27 +189,23 @@ sddmm_tc_kernel(PlanView pv, const int4* __restrict__ groups, int32_t num_groups
     }
   } else {
     // ===================================== producers ====================================
-    const int p = warp - kProducerWarp0;
-    const int pg = p / kProdPerGroup;    // serves stages k == pg (mod kProdGroups)
-    const int pw = p % kProdPerGroup;
+    const int pw = warp - kProducerWarp0;
     constexpr int kRows = 128 + TCGNN_BLK_H;          // gathered rows + the window's own rows
     constexpr int kItems = kRows * 8;                 // 16-byte vectors per stage
-    constexpr int kPerLane = (kItems + kProdPerGroup * 32 - 1) / (kProdPerGroup * 32);   // 9
-    for (int32_t k = pg; k < n_stages; k += kProdGroups) {
+    constexpr int kPerLane = (kItems + kProducers * 32 - 1) / (kProducers * 32);   // 9
+    const int nvec = (dim + 3) >> 2;                  // valid 16-byte vectors per row
+    for (int32_t k = 0; k < n_stages; ++k) {
       const int s = k % kStages;
-      mbar_wait(&meta_full[s], (k / kStages) & 1);
+      mbar_wait(&meta_full[s], (k / kStages) & 1);    // implies empty[s]: the meta loader waited for it
       const uint8_t* ms = m_smem + s * kMetaStageBytes;
       const TileMeta* meta = reinterpret_cast<const TileMeta*>(ms);
       const int4 hdr = *reinterpret_cast<const int4*>(ms + kMetaTileBytes);
       const int32_t ntiles = hdr.y, win = hdr.z, kc = hdr.w;
-      const int32_t f0 = kc * 32;
-      uint8_t* a_stage = a_smem + s * kAStageBytes;
-      uint8_t* b_stage = b_smem + s * kBStageBytes;
-      float4 val[kPerLane];
+      const uint32_t a_stage = smem_u32(a_smem + s * kAStageBytes);
+      const uint32_t b_stage = smem_u32(b_smem + s * kBStageBytes);
 #pragma unroll
       for (int u = 0; u < kPerLane; ++u) {
-        const int item = u * (kProdPerGroup * 32) + pw * 32 + lane;
-        val[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int item = u * (kProducers * 32) + pw * 32 + lane;
         if (item < kItems) {
           const int row = item >> 3, v = item & 7;
           int32_t node = -1;
@@ -214,34 +215,17 @@ sddmm_tc_kernel(PlanView pv, const int4* __restrict__ groups, int32_t num_groups
             node = win * TCGNN_BLK_H + (row - 128);
             node = node < pv.num_nodes ? node + pv.row_base : -1;   // the window's own rows (global ids)
           }
-          const int f = f0 + v * 4;
-          if (node >= 0 && f < dim) {
-            const float* src = x + static_cast<int64_t>(node) * ldx + f;
-            if (vec_ok && f + 4 <= dim) {
-              val[u] = __ldg(reinterpret_cast<const float4*>(src));
-            } else {
-              val[u].x = __ldg(src);
-              if (f + 1 < dim) val[u].y = __ldg(src + 1);
-              if (f + 2 < dim) val[u].z = __ldg(src + 2);
-              if (f + 3 < dim) val[u].w = __ldg(src + 3);
-            }
-          }
+          const int vg = kc * 8 + v;                                // vector index inside the feature row
+          const bool valid = node >= 0 && vg < nvec;
+          const float* src = x + static_cast<int64_t>(valid ? node : 0) * ldx + (valid ? vg * 4 : 0);
+          const uint32_t dst = row < 128 ? a_stage + (row >> 3) * 1024 + sw128_offset(row & 7, v)
+                                         : b_stage + ((row - 128) >> 3) * 1024 + sw128_offset(row & 7, v);
+          cp_async_16(dst, src, valid ? 16u : 0u);                  // padding rows / feature tail: zero-fill
         }
       }
-#pragma unroll
-      for (int u = 0; u < kPerLane; ++u) {
-        const int item = u * (kProdPerGroup * 32) + pw * 32 + lane;
-        if (item < kItems) {
-          const int row = item >> 3, v = item & 7;
-          uint8_t* dst = row < 128 ? a_stage + (row >> 3) * 1024 + sw128_offset(row & 7, v)
-                                   : b_stage + ((row - 128) >> 3) * 1024 + sw128_offset(row & 7, v);
-          *reinterpret_cast<float4*>(dst) = tf32_rna4(val[u]);
-        }
-      }
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&full[s]);
+      cp_async_mbar_arrive_noinc(&full[s]);
     }
+    cp_async_wait_all();
   }
 
   tc_fence_before();
@@ -283,7 +267,10 @@ int sddmm_launch(tcgnn_plan* plan, const float* x, int64_t ldx, float* edge_out,
   int grid = plan->num_sms;
   if (plan->num_groups < grid * 2) grid = plan->num_groups / 2;
   if (grid < 1) grid = 1;
-  const int vec_ok = (reinterpret_cast<uintptr_t>(x) % 16 == 0) && (ldx % 4 == 0);
+  const int64_t ldr = (static_cast<int64_t>(dim) + 3) / 4 * 4;
+  const float* xr = nullptr;
+  st = round_pack_launch(plan, x, ldx, dim, ldr, stream, &xr);
+  if (st != TCGNN_OK) return st;
   if (static_cast<int64_t>(plan->num_pairs) < plan->num_edges) {
     // duplicated (row, col) pairs: only one edge of each pair receives the value (as in the reference)
     e = cudaMemsetAsync(edge_out, 0, sizeof(float) * static_cast<size_t>(plan->num_edges), stream);
@@ -292,8 +279,8 @@ int sddmm_launch(tcgnn_plan* plan, const float* x, int64_t ldx, float* edge_out,
       return TCGNN_ERR_CUDA;
     }
   }
-  sddmm_tc_kernel<<<grid, kThreads, kSmemBytes, stream>>>(plan->view(), plan->groups, plan->num_groups, x, ldx,
-                                                         plan->sddmm_perm, dim, vec_ok);
+  sddmm_tc_kernel<<<grid, kThreads, kSmemBytes, stream>>>(plan->view(), plan->groups, plan->num_groups, xr, ldr,
+                                                         plan->sddmm_perm, dim);
   count_launch();
   int g = (plan->num_pairs + 255) / 256;
   if (g > 148 * 16) g = 148 * 16;

@@ -11,46 +11,64 @@
 // The accumulator lives in TMEM (lane = feature, column = window row); nothing is rescanned:
 // the plan (plan.cu) delivers, per tile, the 8 rows to gather and a 128-bit occupancy mask.
 //
-// CTA = 24 warps, persistent over a contiguous, equally sized slice of the global tile stream
-// (balances hub windows: a window cut by a slice boundary is combined with fp32 atomics):
+// Two kernels per call:
+//   1. tf32_round_pack_kernel (round_pack.cu): Xr = cvt.rna.tf32(X) once per element (the reference
+//      rounds inside its inner loop, TCGNN_kernel.cu:441-443; tcgen05 would otherwise truncate),
+//      packed with a 16-byte aligned leading dimension so every gather below is a 128-bit access;
+//   2. spmm_tc_kernel, CTA = 12 warps, persistent over a contiguous, equally sized slice of the
+//      global tile stream (balances hub windows: a window cut by a slice boundary is combined with
+//      fp32 atomics):
 //   warps 0-3   epilogue     TMEM -> registers -> coalesced global stores (lane = feature)
-//   warp  4     MMA issuer   one elected thread issues tcgen05.mma / tcgen05.commit
+//   warp  4     MMA issuer   one thread issues tcgen05.mma / tcgen05.commit; per stage it reads ONE
+//                            word (which tiles open / close a window) -- it is the only serial
+//                            resource of the CTA, so its per-tile path is kept to a few instructions
 //   warp  5     meta loader  TMA bulk copy (UBLKCP) of the stage's tile records into smem
-//   warps 6-7   B builders   expand occupancy masks (or edge weights) into the K-major B tile
-//   warps 8-23  A producers  128-bit coalesced gathers of X rows, cvt.rna.tf32 in registers,
-//                            st.shared into the swizzled (128B rows, 32B granule) MN-major A tile
-// Pipeline: S stages of G=4 tiles; per stage three mbarriers (meta_full, full, empty); NACC
+//   warps 6-7   B builders   expand occupancy masks (or edge weights) into the K-major B tiles and
+//                            publish the stage's open/close word
+//   warps 8-11  A producers  asynchronous 128-bit gathers (cp.async / LDGSTS, zero-fill for padding)
+//                            of Xr rows straight into the swizzled (128B rows, 32B granule) MN-major
+//                            A tile; completion arrives on the stage's mbarrier, so a producer never
+//                            waits for data and the gathers in flight are bounded by shared memory
+//                            (S stages * G tiles * 4 KB), not by registers.
+// Pipeline: S stages of G tiles; per stage three mbarriers (meta_full, full, empty); NACC
 // TMEM accumulators with acc_full / acc_empty so the epilogue overlaps the next windows.
+// All shared-memory metadata reads are explicit ld.shared (the generic-address loads the compiler
+// emits for a runtime-aligned dynamic smem base cost the MMA thread ~300 cycles per tile).
+#include <stdlib.h>
+
 #include "plan.h"
 
 namespace tcgnn {
 
 namespace {
 
-constexpr int kG = 4;                 // tiles per pipeline stage
 constexpr int kEpiWarps = 4;
 constexpr int kMmaWarp = 4;
 constexpr int kMetaWarp = 5;
 constexpr int kBuilderWarp0 = 6;
 constexpr int kBuilders = 2;
 constexpr int kProducerWarp0 = 8;
-constexpr int kProducers = 16;        // 4 groups of kG warps; group i serves stages k == i (mod 4)
-constexpr int kProducerGroups = kProducers / kG;
+constexpr int kProducers = 4;         // producer warp p gathers tiles p, p+4, ... of every stage
 constexpr int kWarps = kProducerWarp0 + kProducers;
 constexpr int kThreads = kWarps * 32;
 constexpr int kAcc = 4;               // TMEM accumulator ring
 constexpr int kBTileBytes = TCGNN_BLK_H * TCGNN_BLK_W * 4;  // 512
-constexpr int kMetaStageBytes = kG * static_cast<int>(sizeof(TileMeta));
+// ablation switches (env TCGNN_ABLATE, profiling only -- results are wrong when set): skip the row
+// gathers / the MMAs after a window's first / the B-tile construction
+constexpr uint32_t kAblateGather = 1u, kAblateMma = 2u, kAblateBuild = 4u;
 
 template <int DBLK>
 struct Cfg {
+  static constexpr int kG = DBLK == 1 ? 8 : 4;                 // tiles per pipeline stage (32 KB of A)
   static constexpr int kATileBytes = DBLK * 4096;              // DBLK*4 swizzle atoms of 8 rows x 128 B
   static constexpr int kAStageBytes = kG * kATileBytes;
   static constexpr int kBStageBytes = kG * kBTileBytes;
-  static constexpr int kStages = DBLK == 1 ? 10 : 6;
+  static constexpr int kMetaStageBytes = kG * static_cast<int>(sizeof(TileMeta));
+  static constexpr int kStages = 5;
   static constexpr uint32_t kTmemCols = kAcc * DBLK * 16;      // 64 / 128
-  static constexpr int kSmemBytes = kStages * (kAStageBytes + kBStageBytes + kMetaStageBytes) +
-                                    (3 * kStages + 2 * kAcc) * 8 + 16 + 1024 /*alignment slack*/;
+  static constexpr int kBarBytes = (3 * kStages + 2 * kAcc) * 8;
+  static constexpr int kSmemBytes = kStages * (kAStageBytes + kBStageBytes + kMetaStageBytes) + kBarBytes +
+                                    kStages * 4 /*info words*/ + 16 + 1024 /*alignment slack*/;
 };
 
 struct SliceInfo {
@@ -109,22 +127,24 @@ __global__ void permute_weights_kernel(const int32_t* __restrict__ eperm, const 
 
 template <int DBLK>
 __global__ void __launch_bounds__(kThreads, 1)
-spmm_tc_kernel(PlanView pv, const float* __restrict__ x, int64_t ldx, const float* __restrict__ wperm,
-               float* __restrict__ y, int64_t ldy, int32_t dim /* <= DBLK*128, features of this pass */,
-               int vec_ok /* x 16B-aligned and ldx % 4 == 0 */) {
+spmm_tc_kernel(PlanView pv, const float* __restrict__ x /* tf32-rounded, 16B aligned */, int64_t ldx /* % 4 == 0 */,
+               const float* __restrict__ wperm, float* __restrict__ y, int64_t ldy,
+               int32_t dim /* <= DBLK*128, features of this pass */, uint32_t ablate /* kAblate* bits, 0 in production */) {
   using C = Cfg<DBLK>;
+  constexpr int kG = C::kG;
+  constexpr int S = C::kStages;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* a_smem = smem;                                              // [S][G][DBLK*4 atoms][8][128B]
-  uint8_t* b_smem = a_smem + C::kStages * C::kAStageBytes;             // [S][G][512B]
-  uint8_t* m_smem = b_smem + C::kStages * C::kBStageBytes;             // [S][G] TileMeta
-  uint64_t* bars = reinterpret_cast<uint64_t*>(m_smem + C::kStages * kMetaStageBytes);
-  uint64_t* meta_full = bars;
-  uint64_t* full = bars + C::kStages;
-  uint64_t* empty = bars + 2 * C::kStages;
-  uint64_t* acc_full = bars + 3 * C::kStages;
-  uint64_t* acc_empty = acc_full + kAcc;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + kAcc);
+  // shared-space byte addresses (ld.shared / st.shared / descriptors all take these)
+  const uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t a_smem = smem;                                       // [S][G][DBLK*4 atoms][8][128B]
+  const uint32_t b_smem = a_smem + S * C::kAStageBytes;               // [S][G][512B]
+  const uint32_t m_smem = b_smem + S * C::kBStageBytes;               // [S][G] TileMeta
+  const uint32_t bars = m_smem + S * C::kMetaStageBytes;
+  const uint32_t meta_full = bars, full = bars + 8 * S, empty = bars + 16 * S;
+  const uint32_t acc_full = bars + 24 * S, acc_empty = acc_full + 8 * kAcc;
+  const uint32_t info_smem = acc_empty + 8 * kAcc;                    // [S] open/close word per stage
+  const uint32_t tmem_slot = info_smem + 4 * S;
+  uint8_t* const smem_gen = smem_raw + (smem - smem_u32(smem_raw));   // generic view (TMA destination)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -133,14 +153,14 @@ spmm_tc_kernel(PlanView pv, const float* __restrict__ x, int64_t ldx, const floa
   const int32_t n_stages = (n_tiles + kG - 1) / kG;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < C::kStages; ++s) {
-      mbar_init(&meta_full[s], 1);
-      mbar_init(&full[s], kG + 1);   // kG producer warps + 1 builder warp
-      mbar_init(&empty[s], 1);       // tcgen05.commit
+    for (int s = 0; s < S; ++s) {
+      mbar_init(meta_full + 8 * s, 1);
+      mbar_init(full + 8 * s, kProducers * 32 + 1);   // every producer thread (cp.async completion) + 1 builder warp
+      mbar_init(empty + 8 * s, 1);                    // tcgen05.commit
     }
     for (int b = 0; b < kAcc; ++b) {
-      mbar_init(&acc_full[b], 1);            // tcgen05.commit
-      mbar_init(&acc_empty[b], kEpiWarps);   // one arrive per epilogue warp
+      mbar_init(acc_full + 8 * b, 1);                 // tcgen05.commit
+      mbar_init(acc_empty + 8 * b, kEpiWarps);        // one arrive per epilogue warp
     }
     fence_mbar_init();
   }
@@ -148,14 +168,14 @@ spmm_tc_kernel(PlanView pv, const float* __restrict__ x, int64_t ldx, const floa
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = lds_u32(tmem_slot);
 
   if (warp < kEpiWarps) {
     // ===================================== epilogue =====================================
     const int q = warp;  // TMEM lane quadrant == warp id % 4
     for (int32_t wl = 0; wl < sl.n_windows; ++wl) {
       const int b = wl % kAcc;
-      mbar_wait(&acc_full[b], (wl / kAcc) & 1);
+      mbar_wait_backoff(acc_full + 8 * b, (wl / kAcc) & 1);
       tc_fence_after();
       const int32_t w = sl.w_first + wl;
       const bool use_atomic = (wl == 0 && sl.partial_first) || (wl == sl.n_windows - 1 && sl.partial_last);
@@ -181,7 +201,7 @@ spmm_tc_kernel(PlanView pv, const float* __restrict__ x, int64_t ldx, const floa
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[b]);
+      if (lane == 0) mbar_arrive(acc_empty + 8 * b);
     }
   } else if (warp == kMmaWarp) {
     // ===================================== MMA issuer ===================================
@@ -192,52 +212,64 @@ spmm_tc_kernel(PlanView pv, const float* __restrict__ x, int64_t ldx, const floa
       const uint64_t adesc0 = make_smem_desc(0, 1024, 512, kSwizzle128BBase32B);
       // B: K-major, no swizzle: 8x16B core matrices; K chunks 128 B apart (LBO), 8-row groups 256 B apart (SBO)
       const uint64_t bdesc0 = make_smem_desc(0, 128, 256, kSwizzleNone);
+      const bool skip_mma = (ablate & kAblateMma) != 0;
       int32_t wl = 0;
+      uint32_t acc = tmem_base;
       int b = 0;
+      int s = 0;
+      uint32_t ph = 0;
       for (int32_t k = 0; k < n_stages; ++k) {
-        const int s = k % C::kStages;
-        mbar_wait(&full[s], (k / C::kStages) & 1);
+        mbar_wait(full + 8 * s, ph);
+        fence_proxy_async_smem();   // cp.async (generic-proxy) writes of the A tiles -> tcgen05 operand reads
         tc_fence_after();
-        const TileMeta* meta = reinterpret_cast<const TileMeta*>(m_smem + s * kMetaStageBytes);
-        const int32_t g0 = sl.t0 + k * kG;
-        const int nt = min(kG, sl.t1 - g0);
-        for (int j = 0; j < nt; ++j) {
-          const uint32_t flags = meta[j].flags;
-          const bool first = (flags & kTileFirst) != 0 || (g0 + j == sl.t0);
-          const bool last = (flags & kTileLast) != 0 || (g0 + j == sl.t1 - 1);
-          if (first) {
-            b = wl % kAcc;
-            mbar_wait(&acc_empty[b], ((wl / kAcc) & 1) ^ 1);
-            tc_fence_after();
-          }
-          const uint32_t a_addr = smem_u32(a_smem + s * C::kAStageBytes + j * C::kATileBytes);
-          const uint32_t b_addr = smem_u32(b_smem + s * C::kBStageBytes + j * kBTileBytes);
-          const uint64_t bdesc = bdesc0 | static_cast<uint64_t>((b_addr & 0x3FFFFu) >> 4);
+        const uint32_t info = lds_u32(info_smem + 4 * s);   // bits [0,G): tile opens a window, [8,8+G): closes, [16,..): tiles
+        const int nt = static_cast<int>(info >> 16);
+        uint32_t a_addr = a_smem + s * C::kAStageBytes;
+        uint32_t b_addr = b_smem + s * C::kBStageBytes;
 #pragma unroll
-          for (int m = 0; m < DBLK; ++m) {
-            const uint64_t adesc = adesc0 | static_cast<uint64_t>(((a_addr + m * 4096) & 0x3FFFFu) >> 4);
-            umma_tf32(tmem_base + (b * DBLK + m) * 16, adesc, bdesc, idesc, first ? 0u : 1u);
-          }
-          if (last) {
-            umma_commit(&acc_full[b]);
-            ++wl;
+        for (int j = 0; j < kG; ++j) {
+          if (j < nt) {
+            const bool first = (info >> j) & 1u;
+            if (first) {
+              b = wl % kAcc;
+              acc = tmem_base + b * DBLK * 16;
+              mbar_wait(acc_empty + 8 * b, ((wl / kAcc) & 1) ^ 1);
+              tc_fence_after();
+            }
+            if (!skip_mma || first) {
+              const uint64_t bdesc = bdesc0 | static_cast<uint64_t>((b_addr & 0x3FFFFu) >> 4);
+#pragma unroll
+              for (int m = 0; m < DBLK; ++m) {
+                const uint64_t adesc = adesc0 | static_cast<uint64_t>(((a_addr + m * 4096) & 0x3FFFFu) >> 4);
+                umma_tf32(acc + m * 16, adesc, bdesc, idesc, first ? 0u : 1u);
+              }
+            }
+            if ((info >> (8 + j)) & 1u) {
+              umma_commit(acc_full + 8 * b);
+              ++wl;
+            }
+            a_addr += C::kATileBytes;
+            b_addr += kBTileBytes;
           }
         }
-        umma_commit(&empty[s]);
+        umma_commit(empty + 8 * s);
+        if (++s == S) { s = 0; ph ^= 1u; }
       }
       // the last commit must land in this CTA's shared memory before the CTA may retire
-      if (n_stages > 0) mbar_wait(&empty[(n_stages - 1) % C::kStages], ((n_stages - 1) / C::kStages) & 1);
+      if (n_stages > 0) mbar_wait(empty + 8 * ((n_stages - 1) % S), ((n_stages - 1) / S) & 1);
     }
   } else if (warp == kMetaWarp) {
     // ===================================== meta loader (TMA) ============================
     if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
       for (int32_t k = 0; k < n_stages; ++k) {
-        const int s = k % C::kStages;
-        mbar_wait(&empty[s], ((k / C::kStages) & 1) ^ 1);
+        mbar_wait(empty + 8 * s, ph ^ 1u);
         const int32_t g0 = sl.t0 + k * kG;
         const uint32_t bytes = static_cast<uint32_t>(min(kG, sl.t1 - g0)) * sizeof(TileMeta);
-        mbar_arrive_expect_tx(&meta_full[s], bytes);
-        tma_bulk_g2s(m_smem + s * kMetaStageBytes, pv.tiles + g0, bytes, &meta_full[s]);
+        mbar_arrive_expect_tx(meta_full + 8 * s, bytes);
+        tma_bulk_g2s(smem_gen + (m_smem - smem) + s * C::kMetaStageBytes, pv.tiles + g0, bytes, meta_full + 8 * s);
+        if (++s == S) { s = 0; ph ^= 1u; }
       }
     }
   } else if (warp < kProducerWarp0) {
@@ -248,17 +280,30 @@ spmm_tc_kernel(PlanView pv, const float* __restrict__ x, int64_t ldx, const floa
     const int kq = (lane >> 3) & 1;
     const int word = n >> 2;
     const int shift = (n & 3) * 8 + kq * 4;
+    const bool skip = (ablate & kAblateBuild) != 0;
     for (int32_t k = bq; k < n_stages; k += kBuilders) {
-      const int s = k % C::kStages;
-      mbar_wait(&meta_full[s], (k / C::kStages) & 1);
-      const TileMeta* meta = reinterpret_cast<const TileMeta*>(m_smem + s * kMetaStageBytes);
-      const int nt = min(kG, sl.t1 - (sl.t0 + k * kG));
+      const int s = k % S;
+      mbar_wait(meta_full + 8 * s, (k / S) & 1);
+      const uint32_t meta = m_smem + s * C::kMetaStageBytes;
+      const int32_t g0 = sl.t0 + k * kG;
+      const int nt = min(kG, sl.t1 - g0);
+      // open/close word for the MMA thread: lane j looks at tile j
+      {
+        bool first = false, last = false;
+        if (lane < nt) {
+          const uint32_t flags = lds_u32(meta + lane * 64 + 56);
+          first = (flags & kTileFirst) != 0 || (g0 + lane == sl.t0);
+          last = (flags & kTileLast) != 0 || (g0 + lane == sl.t1 - 1);
+        }
+        const uint32_t fm = __ballot_sync(0xffffffffu, first), lm = __ballot_sync(0xffffffffu, last);
+        if (lane == 0) sts_u32(info_smem + 4 * s, fm | (lm << 8) | (static_cast<uint32_t>(nt) << 16));
+      }
       float4 v[kG];
 #pragma unroll
-      for (int j = 0; j < kG; ++j) {   // all loads of the stage first (weighted path: up to 16 in flight)
+      for (int j = 0; j < kG; ++j) {   // all loads of the stage first (weighted path: up to 4*G in flight)
         v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (j < nt) {
-          const uint32_t mw = meta[j].mask[word];
+        if (j < nt && !skip) {
+          const uint32_t mw = lds_u32(meta + j * 64 + 32 + word * 4);
           const uint32_t nib = (mw >> shift) & 0xFu;
           if (wperm == nullptr) {
             v[j].x = (nib & 1u) ? 1.0f : 0.0f;
@@ -268,8 +313,8 @@ spmm_tc_kernel(PlanView pv, const float* __restrict__ x, int64_t ldx, const floa
           } else if (nib != 0u) {
             // rank of the first of my four bits among the tile's set bits (bit order r*8+c)
             int rank = __popc(mw & ((1u << shift) - 1u));
-            for (int i = 0; i < word; ++i) rank += __popc(meta[j].mask[i]);
-            const float* wp = wperm + meta[j].edge_ofs + rank;
+            for (int i = 0; i < word; ++i) rank += __popc(lds_u32(meta + j * 64 + 32 + i * 4));
+            const float* wp = wperm + static_cast<int32_t>(lds_u32(meta + j * 64 + 52)) + rank;
             if (nib & 1u) v[j].x = __ldg(wp++);
             if (nib & 2u) v[j].y = __ldg(wp++);
             if (nib & 4u) v[j].z = __ldg(wp++);
@@ -279,66 +324,65 @@ spmm_tc_kernel(PlanView pv, const float* __restrict__ x, int64_t ldx, const floa
       }
 #pragma unroll
       for (int j = 0; j < kG; ++j)
-        if (j < nt) *reinterpret_cast<float4*>(b_smem + s * C::kBStageBytes + j * kBTileBytes + lane * 16) = v[j];
+        if (j < nt) sts_v4(b_smem + s * C::kBStageBytes + j * kBTileBytes + lane * 16, v[j]);
       fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&full[s]);
+      if (lane == 0) mbar_arrive(full + 8 * s);
     }
   } else {
     // ===================================== A producers ==================================
     const int p = warp - kProducerWarp0;
-    const int grp = p / kG;   // serves stages k == grp (mod kProducerGroups)
-    const int j = p % kG;     // tile slot inside the stage
     const int nvec = (dim + 3) >> 2;          // 16-byte vectors per feature row in this pass
-    const int nvec_shift = (nvec & (nvec - 1)) == 0 ? __ffs(nvec) - 1 : -1;   // power of two: shift, no division
-    for (int32_t k = grp; k < n_stages; k += kProducerGroups) {
-      const int s = k % C::kStages;
-      mbar_wait(&meta_full[s], (k / C::kStages) & 1);
-      const int nt = min(kG, sl.t1 - (sl.t0 + k * kG));
-      if (j < nt) {
-        const TileMeta* meta = reinterpret_cast<const TileMeta*>(m_smem + s * kMetaStageBytes) + j;
-        uint8_t* a_tile = a_smem + s * C::kAStageBytes + j * C::kATileBytes;
-        const int items = 8 * nvec;           // (row r, vector v) pairs, r-major
-        for (int base = 0; base < items; base += 8 * 32) {
-          float4 val[8];
-          int it[8];
+    constexpr int kVecPerLane = DBLK * 8;     // 8 rows x DBLK*32 vectors / 32 lanes
+    const bool skip = (ablate & kAblateGather) != 0;
+    int s = 0;
+    uint32_t ph = 0;
+    for (int32_t k = 0; k < n_stages; ++k) {
+      mbar_wait(meta_full + 8 * s, ph);   // implies empty[s]: the meta loader waited for it
+      const int nt = skip ? 0 : min(kG, sl.t1 - (sl.t0 + k * kG));
 #pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const int item = base + u * 32 + lane;
-            it[u] = item;
-            val[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (item < items) {
-              const int r = nvec_shift >= 0 ? item >> nvec_shift : item / nvec;
-              const int v = item - r * nvec;
-              const int32_t col = meta->cols[r];
-              if (col >= 0) {
-                const float* src = x + static_cast<int64_t>(col) * ldx + v * 4;
-                if (vec_ok && v * 4 + 4 <= dim) {
-                  val[u] = __ldg(reinterpret_cast<const float4*>(src));
-                } else {
-                  if (v * 4 + 0 < dim) val[u].x = __ldg(src + 0);
-                  if (v * 4 + 1 < dim) val[u].y = __ldg(src + 1);
-                  if (v * 4 + 2 < dim) val[u].z = __ldg(src + 2);
-                  if (v * 4 + 3 < dim) val[u].w = __ldg(src + 3);
-                }
+      for (int j = p; j < kG; j += kProducers) {
+        if (j < nt) {
+          const uint32_t meta = m_smem + s * C::kMetaStageBytes + j * 64;
+          const uint32_t a_tile = a_smem + s * C::kAStageBytes + j * C::kATileBytes;
+          const int4 c0 = lds_v4(meta), c1 = lds_v4(meta + 16);   // the 8 rows to gather (-1: padding)
+          const int32_t cols[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+          if (nvec == DBLK * 32) {
+            // full-width rows: lane -> vector `lane` (+32) of each of the 8 gathered rows
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+              const int32_t col = cols[r];
+              const float* src = x + static_cast<int64_t>(col < 0 ? 0 : col) * ldx;
+              const uint32_t bytes = col < 0 ? 0u : 16u;   // padding column: zero-fill
+#pragma unroll
+              for (int h = 0; h < DBLK; ++h) {
+                const int v = h * 32 + lane;
+                cp_async_16(a_tile + (v >> 3) * 1024 + sw128_base32_offset(r, v & 7), src + v * 4, bytes);
+              }
+            }
+          } else {
+            // narrow rows (dim < DBLK*128): (row, vector) pairs r-major over the warp
+            const int items = 8 * nvec;
+#pragma unroll
+            for (int u = 0; u < kVecPerLane; ++u) {
+              const int item = u * 32 + lane;
+              if (item < items) {
+                const int r = item / nvec;
+                const int v = item - r * nvec;
+                int32_t col = cols[0];
+#pragma unroll
+                for (int i = 1; i < 8; ++i) col = r == i ? cols[i] : col;
+                const float* src = x + static_cast<int64_t>(col < 0 ? 0 : col) * ldx + v * 4;
+                cp_async_16(a_tile + (v >> 3) * 1024 + sw128_base32_offset(r, v & 7), src, col < 0 ? 0u : 16u);
               }
             }
           }
-#pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const int item = it[u];
-            if (item < items) {
-              const int r = nvec_shift >= 0 ? item >> nvec_shift : item / nvec;
-              const int v = item - r * nvec;
-              *reinterpret_cast<float4*>(a_tile + (v >> 3) * 1024 + sw128_base32_offset(r, v & 7)) = tf32_rna4(val[u]);
-            }
-          }
         }
-        fence_proxy_async_smem();
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&full[s]);
+      cp_async_mbar_arrive_noinc(full + 8 * s);   // fires once this thread's copies have landed
+      if (++s == S) { s = 0; ph ^= 1u; }
     }
+    cp_async_wait_all();
   }
 
   // ===================================== teardown =======================================
@@ -350,8 +394,16 @@ spmm_tc_kernel(PlanView pv, const float* __restrict__ x, int64_t ldx, const floa
   }
 }
 
+uint32_t ablate_flags() {
+  static const uint32_t flags = [] {
+    const char* e = getenv("TCGNN_ABLATE");
+    return e ? static_cast<uint32_t>(strtoul(e, nullptr, 0)) : 0u;
+  }();
+  return flags;
+}
+
 template <int DBLK>
-cudaError_t launch_pass(const tcgnn_plan* plan, int grid, const float* x, int64_t ldx, const float* wperm, float* y,
+cudaError_t launch_pass(const tcgnn_plan* plan, int grid, const float* xr, int64_t ldr, const float* wperm, float* y,
                         int64_t ldy, int32_t dim, cudaStream_t stream) {
   using C = Cfg<DBLK>;
   static bool attr_set[64] = {};
@@ -362,10 +414,10 @@ cudaError_t launch_pass(const tcgnn_plan* plan, int grid, const float* x, int64_
     if (e != cudaSuccess) return e;
     attr_set[dev] = true;
   }
-  const int vec_ok = (reinterpret_cast<uintptr_t>(x) % 16 == 0) && (ldx % 4 == 0);
   spmm_zero_partial_rows<<<grid, 128, 0, stream>>>(plan->view(), y, ldy, dim);
   count_launch();
-  spmm_tc_kernel<DBLK><<<grid, kThreads, C::kSmemBytes, stream>>>(plan->view(), x, ldx, wperm, y, ldy, dim, vec_ok);
+  spmm_tc_kernel<DBLK><<<grid, kThreads, C::kSmemBytes, stream>>>(plan->view(), xr, ldr, wperm, y, ldy, dim,
+                                                                   ablate_flags());
   count_launch();
   return cudaGetLastError();
 }
@@ -386,14 +438,21 @@ int spmm_launch(tcgnn_plan* plan, const float* x, int64_t ldx, const float* edge
     count_launch();
     wperm = plan->weight_perm;
   }
+  // Xr = tf32_rna(X), packed [num_cols, ldr] with ldr % 4 == 0 (16-byte aligned rows)
+  const int64_t ldr = (static_cast<int64_t>(dim) + 3) / 4 * 4;
+  const float* xr = nullptr;
+  {
+    int st = round_pack_launch(plan, x, ldx, dim, ldr, stream, &xr);
+    if (st != TCGNN_OK) return st;
+  }
   // one CTA per SM, each owning an equal slice of the tile stream (>= 8 tiles per CTA)
   int grid = plan->num_sms;
   if (plan->num_tiles < grid * 8) grid = plan->num_tiles / 8;
   if (grid < 1) grid = 1;
   for (int32_t f0 = 0; f0 < dim; f0 += 256) {
     const int32_t d = dim - f0 < 256 ? dim - f0 : 256;
-    cudaError_t e = d > 128 ? launch_pass<2>(plan, grid, x + f0, ldx, wperm, y + f0, ldy, d, stream)
-                            : launch_pass<1>(plan, grid, x + f0, ldx, wperm, y + f0, ldy, d, stream);
+    cudaError_t e = d > 128 ? launch_pass<2>(plan, grid, xr + f0, ldr, wperm, y + f0, ldy, d, stream)
+                            : launch_pass<1>(plan, grid, xr + f0, ldr, wperm, y + f0, ldy, d, stream);
     if (e != cudaSuccess) {
       set_last_error("spmm kernel launch failed: %s", cudaGetErrorString(e));
       return TCGNN_ERR_CUDA;
