@@ -165,6 +165,33 @@ __device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gmem_sr
 __device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
   tma_bulk_g2s(smem_dst, gmem_src, bytes, smem_u32(bar));
 }
+// same, destination given as a shared-window address, with an L2 eviction policy (createpolicy)
+__device__ __forceinline__ void tma_bulk_g2s_hint(uint32_t smem_dst, const void* gmem_src, uint32_t bytes, uint32_t bar,
+                                                  uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+          smem_dst),
+      "l"(gmem_src), "r"(bytes), "r"(bar), "l"(policy)
+      : "memory");
+}
+
+// L2 eviction policies: feature rows are re-read by many windows (keep), the tile stream and the
+// output are touched once (let them go first)
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_normal() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
 
 // ---------------------------------------------------------------------------------------------
 // cp.async (SASS: LDGSTS): 16-byte global -> shared copies that bypass registers; completion is
@@ -173,6 +200,12 @@ __device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gmem_sr
 // src_bytes < 16: the remainder of the 16 bytes is zero-filled (src_bytes == 0 reads nothing)
 __device__ __forceinline__ void cp_async_16(uint32_t smem_dst, const void* gmem_src, uint32_t src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_dst), "l"(gmem_src), "r"(src_bytes)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_16_hint(uint32_t smem_dst, const void* gmem_src, uint32_t src_bytes,
+                                                 uint64_t policy) {
+  asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2, %3;" ::"r"(smem_dst), "l"(gmem_src),
+               "r"(src_bytes), "l"(policy)
                : "memory");
 }
 // one arrival on `bar` (counted in its init count: .noinc) once all prior cp.async of this thread landed

@@ -10,14 +10,22 @@
 // A (gathered rows) and as B (the window's own 16 rows).  Only positions that are edges are
 // written (tile occupancy mask), in tile order; a second pass restores CSR edge order.
 //
-// A pipeline stage is one 32-feature chunk of one group: A 16 KB + B 2 KB + the group's 16 tile
-// records (TMA bulk copy).  X is first rounded to tf32 (cvt.rna) and packed once per call
-// (round_pack.cu), so the row gathers are plain asynchronous copies.  CTA = 10 warps:
+// A pipeline stage is one 32-feature chunk of one group: A 16 KB + B 2 KB.  The group's 16 tile records
+// travel once per group through their own ring (TMA bulk copy), far ahead of the data.  X is first rounded
+// to tf32 (cvt.rna) and packed once per call (round_pack.cu), so the row gathers are plain asynchronous
+// copies.  CTA = 10 warps:
 //   warps 0-3  epilogue     TMEM -> registers -> masked scatter of edge values
-//   warp  4    MMA issuer   warp 5  meta loader (TMA)
+//   warp  4    MMA issuer   (warp-uniform loop, one elected lane issues)
+//   warp  5    meta loader  (TMA)
 //   warps 6-9  producers    cp.async (LDGSTS, zero-fill) of 128 gathered rows + the window's 16 rows,
-//                           32 features each, into the 128B-swizzled K-major images; completion
-//                           arrives on the stage's mbarrier (producers run up to kStages ahead)
+//                           32 features each, into the 128B-swizzled K-major images.  A thread keeps its
+//                           nine row ids in registers for all chunks of a group; every stage is one
+//                           cp.async group, and a warp publishes stage k - kLag with ONE mbarrier arrive
+//                           once cp.async.wait_group says its copies have landed (per-thread
+//                           cp.async.mbarrier arrivals -- 128 per stage -- serialise in the LSU and were the
+//                           bottleneck of the first version of this pipeline).
+#include <stdlib.h>
+
 #include "plan.h"
 
 namespace tcgnn {
@@ -25,6 +33,8 @@ namespace tcgnn {
 namespace {
 
 constexpr int kStages = 10;
+constexpr int kLag = 7;                                   // stages a producer keeps in flight (<= kStages - 1)
+constexpr int kMetaStages = 8;                            // ring of group records
 constexpr int kEpiWarps = 4;
 constexpr int kMmaWarp = 4;
 constexpr int kMetaWarp = 5;
@@ -37,10 +47,13 @@ constexpr int kGroupTiles = 16;
 constexpr int kAStageBytes = 128 * 128;                    // 128 rows x 32 floats
 constexpr int kBStageBytes = TCGNN_BLK_H * 128;            // 16 rows x 32 floats
 constexpr int kMetaTileBytes = kGroupTiles * static_cast<int>(sizeof(TileMeta));
-constexpr int kMetaStageBytes = kMetaTileBytes + 16;       // + header {tile_start, ntiles, win, kc}
+constexpr int kMetaStageBytes = kMetaTileBytes + 16;       // + header {tile_start, ntiles, win, 0}
 constexpr uint32_t kTmemCols = kAcc * 16;
-constexpr int kSmemBytes = kStages * (kAStageBytes + kBStageBytes + kMetaStageBytes) + (3 * kStages + 2 * kAcc) * 8 +
-                           16 + 1024;
+constexpr int kSmemBytes = kStages * (kAStageBytes + kBStageBytes) + kMetaStages * kMetaStageBytes +
+                           (2 * kMetaStages + 2 * kStages + 2 * kAcc) * 8 + 16 + 1024;
+static_assert(kLag <= kStages - 1, "a producer must signal stage k-kLag before it needs slot k-kStages");
+static_assert(kSmemBytes <= 232448, "exceeds the 227 KB of dynamic shared memory per CTA");
+constexpr uint32_t kTuneXLast = 16u;                       // env TCGNN_TUNE: gathers with L2 evict_last
 
 // groups [g_lo, g_hi) of this CTA: equal shares of the tile stream, cut at group boundaries
 __device__ __forceinline__ int32_t first_group_at_or_after(const int4* __restrict__ groups, int32_t num_groups,
@@ -56,19 +69,18 @@ __device__ __forceinline__ int32_t first_group_at_or_after(const int4* __restric
 __global__ void __launch_bounds__(kThreads, 1)
 sddmm_tc_kernel(PlanView pv, const int4* __restrict__ groups, int32_t num_groups,
                 const float* __restrict__ x /* tf32-rounded, 16B aligned */, int64_t ldx /* % 4 == 0 */,
-                float* __restrict__ out_perm, int32_t dim) {
+                float* __restrict__ out_perm, int32_t dim, uint32_t flags) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* a_smem = smem;
-  uint8_t* b_smem = a_smem + kStages * kAStageBytes;
-  uint8_t* m_smem = b_smem + kStages * kBStageBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(m_smem + kStages * kMetaStageBytes);
-  uint64_t* meta_full = bars;
-  uint64_t* full = bars + kStages;
-  uint64_t* empty = bars + 2 * kStages;
-  uint64_t* acc_full = bars + 3 * kStages;
-  uint64_t* acc_empty = acc_full + kAcc;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + kAcc);
+  const uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t a_smem = smem;
+  const uint32_t b_smem = a_smem + kStages * kAStageBytes;
+  const uint32_t m_smem = b_smem + kStages * kBStageBytes;
+  const uint32_t bars = m_smem + kMetaStages * kMetaStageBytes;
+  const uint32_t meta_full = bars, meta_empty = bars + 8 * kMetaStages;
+  const uint32_t full = bars + 16 * kMetaStages, empty = full + 8 * kStages;
+  const uint32_t acc_full = empty + 8 * kStages, acc_empty = acc_full + 8 * kAcc;
+  const uint32_t tmem_slot = acc_empty + 8 * kAcc;
+  uint8_t* const smem_gen = smem_raw + (smem - smem_u32(smem_raw));   // generic view (header store)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -81,14 +93,17 @@ sddmm_tc_kernel(PlanView pv, const int4* __restrict__ groups, int32_t num_groups
   const int32_t n_stages = n_groups * nkc;
 
   if (threadIdx.x == 0) {
+    for (int s = 0; s < kMetaStages; ++s) {
+      mbar_init(meta_full + 8 * s, 1);
+      mbar_init(meta_empty + 8 * s, kProducers);   // every producer warp has taken its row ids
+    }
     for (int s = 0; s < kStages; ++s) {
-      mbar_init(&meta_full[s], 1);
-      mbar_init(&full[s], kProducers * 32);   // every producer thread, on completion of its cp.async copies
-      mbar_init(&empty[s], 1);
+      mbar_init(full + 8 * s, kProducers);         // one arrive per producer warp once its copies have landed
+      mbar_init(empty + 8 * s, 1);                 // tcgen05.commit
     }
     for (int b = 0; b < kAcc; ++b) {
-      mbar_init(&acc_full[b], 1);
-      mbar_init(&acc_empty[b], kEpiWarps);
+      mbar_init(acc_full + 8 * b, 1);
+      mbar_init(acc_empty + 8 * b, kEpiWarps);
     }
     fence_mbar_init();
   }
@@ -96,7 +111,7 @@ sddmm_tc_kernel(PlanView pv, const int4* __restrict__ groups, int32_t num_groups
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = lds_u32(tmem_slot);
 
   if (warp < kEpiWarps) {
     // ===================================== epilogue =====================================
@@ -113,14 +128,14 @@ sddmm_tc_kernel(PlanView pv, const int4* __restrict__ groups, int32_t num_groups
         edge_ofs = t->edge_ofs;
       }
       const int b = gl % kAcc;
-      mbar_wait(&acc_full[b], (gl / kAcc) & 1);
+      mbar_wait_backoff(acc_full + 8 * b, (gl / kAcc) & 1);
       tc_fence_after();
       uint32_t v[16];
       tmem_ld_32x32b_x16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + b * 16, v);
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[b]);
+      if (lane == 0) mbar_arrive(acc_empty + 8 * b);
       // bit (r*8+c): word r/4, bit (r%4)*8+c ; rank in bit order = position in tile-ordered output
       const uint32_t mw[4] = {mask.x, mask.y, mask.z, mask.w};
       int base_rank = 0;
@@ -139,52 +154,59 @@ sddmm_tc_kernel(PlanView pv, const int4* __restrict__ groups, int32_t num_groups
     }
   } else if (warp == kMmaWarp) {
     // ===================================== MMA issuer ===================================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_tf32(128, 16, false, false);
-      // K-major, 128B swizzle: 8-row groups 1024 B apart (SBO); K steps advance the start address by 32 B
-      const uint64_t desc0 = make_smem_desc(0, 16, 1024, kSwizzle128B);
-      for (int32_t k = 0; k < n_stages; ++k) {
-        const int s = k % kStages;
-        const int32_t gl = k / nkc, kc = k - gl * nkc;
-        const int b = gl % kAcc;
-        if (kc == 0) {
-          mbar_wait(&acc_empty[b], ((gl / kAcc) & 1) ^ 1);
-          tc_fence_after();
-        }
-        mbar_wait(&full[s], (k / kStages) & 1);
-        fence_proxy_async_smem();   // cp.async (generic proxy) writes -> tcgen05 operand reads
+    // warp-uniform loop, one elected lane issues
+    constexpr uint32_t idesc = make_idesc_tf32(128, 16, false, false);
+    // K-major, 128B swizzle: 8-row groups 1024 B apart (SBO); K steps advance the start address by 32 B
+    const uint64_t desc0 = make_smem_desc(0, 16, 1024, kSwizzle128B);
+    int s = 0;
+    uint32_t ph = 0;
+    int32_t kc = 0, gl = 0;
+    for (int32_t k = 0; k < n_stages; ++k) {
+      const int b = gl % kAcc;
+      if (kc == 0) {
+        mbar_wait(acc_empty + 8 * b, ((gl / kAcc) & 1) ^ 1);
         tc_fence_after();
-        const uint32_t a_addr = smem_u32(a_smem + s * kAStageBytes);
-        const uint32_t b_addr = smem_u32(b_smem + s * kBStageBytes);
-        const int ksteps = min(4, (dim - kc * 32 + 7) >> 3);
-        for (int ks = 0; ks < ksteps; ++ks) {
-          const uint64_t adesc = desc0 | static_cast<uint64_t>(((a_addr + ks * 32) & 0x3FFFFu) >> 4);
-          const uint64_t bdesc = desc0 | static_cast<uint64_t>(((b_addr + ks * 32) & 0x3FFFFu) >> 4);
-          umma_tf32(tmem_base + b * 16, adesc, bdesc, idesc, (kc | ks) != 0 ? 1u : 0u);
-        }
-        umma_commit(&empty[s]);
-        if (kc == nkc - 1) umma_commit(&acc_full[b]);
       }
-      // the last commit must land in this CTA's shared memory before the CTA may retire
-      if (n_stages > 0) mbar_wait(&empty[(n_stages - 1) % kStages], ((n_stages - 1) / kStages) & 1);
+      mbar_wait(full + 8 * s, ph);   // producers fenced their generic-proxy writes before arriving
+      tc_fence_after();
+      const uint64_t adesc = desc0 | static_cast<uint64_t>(((a_smem + s * kAStageBytes) & 0x3FFFFu) >> 4);
+      const uint64_t bdesc = desc0 | static_cast<uint64_t>(((b_smem + s * kBStageBytes) & 0x3FFFFu) >> 4);
+      const int ksteps = min(4, (dim - kc * 32 + 7) >> 3);
+      if (elect_one()) {
+        if (ksteps == 4) {
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)
+            umma_tf32(tmem_base + b * 16, adesc + static_cast<uint64_t>(ks * 2), bdesc + static_cast<uint64_t>(ks * 2),
+                      idesc, (kc | ks) != 0 ? 1u : 0u);
+        } else {
+          for (int ks = 0; ks < ksteps; ++ks)
+            umma_tf32(tmem_base + b * 16, adesc + static_cast<uint64_t>(ks * 2), bdesc + static_cast<uint64_t>(ks * 2),
+                      idesc, (kc | ks) != 0 ? 1u : 0u);
+        }
+        umma_commit(empty + 8 * s);
+        if (kc == nkc - 1) umma_commit(acc_full + 8 * b);
+      }
+      if (++kc == nkc) { kc = 0; ++gl; }
+      if (++s == kStages) { s = 0; ph ^= 1u; }
     }
+    // the last commit must land in this CTA's shared memory before the CTA may retire
+    if (n_stages > 0) mbar_wait(empty + 8 * ((n_stages - 1) % kStages), ((n_stages - 1) / kStages) & 1);
   } else if (warp == kMetaWarp) {
     // ===================================== meta loader (TMA) ============================
     if (lane == 0) {
       int4 nxt = n_groups > 0 ? groups[g_lo] : make_int4(0, 0, 0, 0);
+      int ms = 0;
+      uint32_t mph = 0;
       for (int32_t gl = 0; gl < n_groups; ++gl) {
         const int4 grp = nxt;
         if (gl + 1 < n_groups) nxt = groups[g_lo + gl + 1];   // prefetch the next work unit
-        for (int32_t kc = 0; kc < nkc; ++kc) {
-          const int32_t k = gl * nkc + kc;
-          const int s = k % kStages;
-          mbar_wait(&empty[s], ((k / kStages) & 1) ^ 1);
-          uint8_t* ms = m_smem + s * kMetaStageBytes;
-          *reinterpret_cast<int4*>(ms + kMetaTileBytes) = make_int4(grp.x, grp.y, grp.z, kc);
-          const uint32_t bytes = static_cast<uint32_t>(grp.y) * sizeof(TileMeta);
-          mbar_arrive_expect_tx(&meta_full[s], bytes);
-          tma_bulk_g2s(ms, pv.tiles + grp.x, bytes, &meta_full[s]);
-        }
+        mbar_wait(meta_empty + 8 * ms, mph ^ 1u);
+        *reinterpret_cast<int4*>(smem_gen + (m_smem - smem) + ms * kMetaStageBytes + kMetaTileBytes) =
+            make_int4(grp.x, grp.y, grp.z, 0);                // ordered before the readers by the arrive below
+        const uint32_t bytes = static_cast<uint32_t>(grp.y) * sizeof(TileMeta);
+        mbar_arrive_expect_tx(meta_full + 8 * ms, bytes);
+        tma_bulk_g2s(smem_gen + (m_smem - smem) + ms * kMetaStageBytes, pv.tiles + grp.x, bytes, meta_full + 8 * ms);
+        if (++ms == kMetaStages) { ms = 0; mph ^= 1u; }
       }
     }
   } else {
@@ -194,38 +216,67 @@ sddmm_tc_kernel(PlanView pv, const int4* __restrict__ groups, int32_t num_groups
     constexpr int kItems = kRows * 8;                 // 16-byte vectors per stage
     constexpr int kPerLane = (kItems + kProducers * 32 - 1) / (kProducers * 32);   // 9
     const int nvec = (dim + 3) >> 2;                  // valid 16-byte vectors per row
-    for (int32_t k = 0; k < n_stages; ++k) {
-      const int s = k % kStages;
-      mbar_wait(&meta_full[s], (k / kStages) & 1);    // implies empty[s]: the meta loader waited for it
-      const uint8_t* ms = m_smem + s * kMetaStageBytes;
-      const TileMeta* meta = reinterpret_cast<const TileMeta*>(ms);
-      const int4 hdr = *reinterpret_cast<const int4*>(ms + kMetaTileBytes);
-      const int32_t ntiles = hdr.y, win = hdr.z, kc = hdr.w;
-      const uint32_t a_stage = smem_u32(a_smem + s * kAStageBytes);
-      const uint32_t b_stage = smem_u32(b_smem + s * kBStageBytes);
+    const uint64_t policy = (flags & kTuneXLast) ? l2_policy_evict_last() : l2_policy_evict_normal();
+    int s = 0, ms = 0;
+    uint32_t ph = 0, mph = 0;
+    int32_t k = 0;
+    for (int32_t gl = 0; gl < n_groups; ++gl) {
+      // this thread's rows of the group: the same (row, vector) items in every feature chunk
+      mbar_wait(meta_full + 8 * ms, mph);
+      const uint32_t meta = m_smem + ms * kMetaStageBytes;
+      const int4 hdr = lds_v4(meta + kMetaTileBytes);
+      const int32_t ntiles = hdr.y, win = hdr.z;
+      int32_t node[kPerLane];
 #pragma unroll
       for (int u = 0; u < kPerLane; ++u) {
         const int item = u * (kProducers * 32) + pw * 32 + lane;
+        const int row = item >> 3;
+        node[u] = -1;
         if (item < kItems) {
-          const int row = item >> 3, v = item & 7;
-          int32_t node = -1;
           if (row < 128) {
-            if ((row >> 3) < ntiles) node = meta[row >> 3].cols[row & 7];
+            if ((row >> 3) < ntiles) node[u] = static_cast<int32_t>(lds_u32(meta + (row >> 3) * 64 + (row & 7) * 4));
           } else {
-            node = win * TCGNN_BLK_H + (row - 128);
-            node = node < pv.num_nodes ? node + pv.row_base : -1;   // the window's own rows (global ids)
+            const int32_t r = win * TCGNN_BLK_H + (row - 128);
+            node[u] = r < pv.num_nodes ? r + pv.row_base : -1;   // the window's own rows (global ids)
           }
-          const int vg = kc * 8 + v;                                // vector index inside the feature row
-          const bool valid = node >= 0 && vg < nvec;
-          const float* src = x + static_cast<int64_t>(valid ? node : 0) * ldx + (valid ? vg * 4 : 0);
-          const uint32_t dst = row < 128 ? a_stage + (row >> 3) * 1024 + sw128_offset(row & 7, v)
-                                         : b_stage + ((row - 128) >> 3) * 1024 + sw128_offset(row & 7, v);
-          cp_async_16(dst, src, valid ? 16u : 0u);                  // padding rows / feature tail: zero-fill
         }
       }
-      cp_async_mbar_arrive_noinc(&full[s]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(meta_empty + 8 * ms);
+      if (++ms == kMetaStages) { ms = 0; mph ^= 1u; }
+      for (int32_t kc = 0; kc < nkc; ++kc, ++k) {
+        mbar_wait(empty + 8 * s, ph ^ 1u);             // slot consumed by the MMAs of stage k - kStages
+        const uint32_t a_stage = a_smem + s * kAStageBytes;
+        const uint32_t b_stage = b_smem + s * kBStageBytes;
+#pragma unroll
+        for (int u = 0; u < kPerLane; ++u) {
+          const int item = u * (kProducers * 32) + pw * 32 + lane;
+          if (item < kItems) {
+            const int row = item >> 3, v = item & 7;
+            const int vg = kc * 8 + v;                               // vector index inside the feature row
+            const bool valid = node[u] >= 0 && vg < nvec;
+            const float* src = x + static_cast<int64_t>(valid ? node[u] : 0) * ldx + (valid ? vg * 4 : 0);
+            const uint32_t dst = row < 128 ? a_stage + (row >> 3) * 1024 + sw128_offset(row & 7, v)
+                                           : b_stage + ((row - 128) >> 3) * 1024 + sw128_offset(row & 7, v);
+            cp_async_16_hint(dst, src, valid ? 16u : 0u, policy);    // padding rows / feature tail: zero-fill
+          }
+        }
+        cp_async_commit_group();
+        if (k >= kLag) {
+          // the copies of stage k - kLag have landed: publish them (writer-side proxy fence, one arrive per warp)
+          cp_async_wait_group<kLag>();
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(full + 8 * ((k - kLag) % kStages));
+        }
+        if (++s == kStages) { s = 0; ph ^= 1u; }
+      }
     }
     cp_async_wait_all();
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0)
+      for (int32_t j = n_stages > kLag ? n_stages - kLag : 0; j < n_stages; ++j) mbar_arrive(full + 8 * (j % kStages));
   }
 
   tc_fence_before();
@@ -279,8 +330,12 @@ int sddmm_launch(tcgnn_plan* plan, const float* x, int64_t ldx, float* edge_out,
       return TCGNN_ERR_CUDA;
     }
   }
+  static const uint32_t flags = [] {
+    const char* t = getenv("TCGNN_TUNE");
+    return t ? static_cast<uint32_t>(strtoul(t, nullptr, 0)) & kTuneXLast : kTuneXLast;
+  }();
   sddmm_tc_kernel<<<grid, kThreads, kSmemBytes, stream>>>(plan->view(), plan->groups, plan->num_groups, xr, ldr,
-                                                         plan->sddmm_perm, dim);
+                                                         plan->sddmm_perm, dim, flags);
   count_launch();
   int g = (plan->num_pairs + 255) / 256;
   if (g > 148 * 16) g = 148 * 16;

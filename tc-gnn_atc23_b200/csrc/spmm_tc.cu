@@ -19,19 +19,23 @@
 //      global tile stream (balances hub windows: a window cut by a slice boundary is combined with
 //      fp32 atomics):
 //   warps 0-3   epilogue     TMEM -> registers -> coalesced global stores (lane = feature)
-//   warp  4     MMA issuer   one thread issues tcgen05.mma / tcgen05.commit; per stage it reads ONE
-//                            word (which tiles open / close a window) -- it is the only serial
-//                            resource of the CTA, so its per-tile path is kept to a few instructions
-//   warp  5     meta loader  TMA bulk copy (UBLKCP) of the stage's tile records into smem
+//   warp  4     MMA issuer   warp-uniform loop, one elected lane issues tcgen05.mma / tcgen05.commit; per
+//                            stage it reads ONE word (which tiles open / close a window); a full stage
+//                            inside one window is G back-to-back MMAs with precomputed descriptors
+//   warp  5     meta loader  TMA bulk copies (UBLKCP, L2 evict_first) of the tile records into a 16-deep
+//                            ring that runs far ahead of the data stages
 //   warps 6-7   B builders   expand occupancy masks (or edge weights) into the K-major B tiles and
 //                            publish the stage's open/close word
-//   warps 8-11  A producers  asynchronous 128-bit gathers (cp.async / LDGSTS, zero-fill for padding)
-//                            of Xr rows straight into the swizzled (128B rows, 32B granule) MN-major
-//                            A tile; completion arrives on the stage's mbarrier, so a producer never
-//                            waits for data and the gathers in flight are bounded by shared memory
-//                            (S stages * G tiles * 4 KB), not by registers.
-// Pipeline: S stages of G tiles; per stage three mbarriers (meta_full, full, empty); NACC
-// TMEM accumulators with acc_full / acc_empty so the epilogue overlaps the next windows.
+//   warps 8-11  A producers  asynchronous 128-bit gathers (cp.async / LDGSTS, zero-fill for padding,
+//                            L2 evict_last) of Xr rows straight into the swizzled (128B rows, 32B granule)
+//                            MN-major A tile.  Every stage is one cp.async group per thread; a warp
+//                            publishes stage k - kLag with ONE mbarrier arrive once cp.async.wait_group
+//                            says its copies have landed, so kLag stages (128 KB) of gathers are in flight
+//                            per SM and a stage costs 5 barrier arrivals (the first version used
+//                            per-thread cp.async.mbarrier arrivals: 128 serialised arrivals per stage were
+//                            60-70 % of the kernel time, profiles/r01b_ablations.txt).
+// Pipeline: S data stages of G tiles (A + B), three mbarrier rings (meta_full/meta_empty, full/empty);
+// NACC TMEM accumulators with acc_full / acc_empty so the epilogue overlaps the next windows.
 // All shared-memory metadata reads are explicit ld.shared (the generic-address loads the compiler
 // emits for a runtime-aligned dynamic smem base cost the MMA thread ~300 cycles per tile).
 #include <stdlib.h>
@@ -56,6 +60,10 @@ constexpr int kBTileBytes = TCGNN_BLK_H * TCGNN_BLK_W * 4;  // 512
 // ablation switches (env TCGNN_ABLATE, profiling only -- results are wrong when set): skip the row
 // gathers / the MMAs after a window's first / the B-tile construction
 constexpr uint32_t kAblateGather = 1u, kAblateMma = 2u, kAblateBuild = 4u;
+// L2 policy switches (env TCGNN_TUNE overrides the default kTuneDefault): feature-row gathers evict_last /
+// tile stream evict_first / output rows written with streaming stores
+constexpr uint32_t kTuneXLast = 16u, kTuneMetaFirst = 32u, kTuneYStream = 64u;
+constexpr uint32_t kTuneDefault = kTuneXLast | kTuneMetaFirst | kTuneYStream;
 
 template <int DBLK>
 struct Cfg {
@@ -64,11 +72,15 @@ struct Cfg {
   static constexpr int kAStageBytes = kG * kATileBytes;
   static constexpr int kBStageBytes = kG * kBTileBytes;
   static constexpr int kMetaStageBytes = kG * static_cast<int>(sizeof(TileMeta));
-  static constexpr int kStages = 5;
+  static constexpr int kStages = 6;                            // data ring (A + B tiles)
+  static constexpr int kLag = 4;                               // stages a producer keeps in flight (<= kStages - 1)
+  static constexpr int kMetaStages = 16;                       // tile-record ring, prefetched far ahead of the data
   static constexpr uint32_t kTmemCols = kAcc * DBLK * 16;      // 64 / 128
-  static constexpr int kBarBytes = (3 * kStages + 2 * kAcc) * 8;
-  static constexpr int kSmemBytes = kStages * (kAStageBytes + kBStageBytes + kMetaStageBytes) + kBarBytes +
-                                    kStages * 4 /*info words*/ + 16 + 1024 /*alignment slack*/;
+  static constexpr int kBarBytes = (2 * kMetaStages + 2 * kStages + 2 * kAcc) * 8;
+  static constexpr int kSmemBytes = kStages * (kAStageBytes + kBStageBytes) + kMetaStages * kMetaStageBytes +
+                                    kBarBytes + kStages * 4 /*info words*/ + 16 + 1024 /*alignment slack*/;
+  static_assert(kLag <= kStages - 1, "a producer must be able to signal stage k-kLag before it needs slot k-kStages");
+  static_assert(kSmemBytes <= 232448, "exceeds the 227 KB of dynamic shared memory per CTA");
 };
 
 struct SliceInfo {
@@ -129,22 +141,24 @@ template <int DBLK>
 __global__ void __launch_bounds__(kThreads, 1)
 spmm_tc_kernel(PlanView pv, const float* __restrict__ x /* tf32-rounded, 16B aligned */, int64_t ldx /* % 4 == 0 */,
                const float* __restrict__ wperm, float* __restrict__ y, int64_t ldy,
-               int32_t dim /* <= DBLK*128, features of this pass */, uint32_t ablate /* kAblate* bits, 0 in production */) {
+               int32_t dim /* <= DBLK*128, features of this pass */, uint32_t flags /* kAblate* | kTune* bits */) {
   using C = Cfg<DBLK>;
   constexpr int kG = C::kG;
   constexpr int S = C::kStages;
+  constexpr int MS = C::kMetaStages;
+  constexpr int L = C::kLag;
   extern __shared__ uint8_t smem_raw[];
-  // shared-space byte addresses (ld.shared / st.shared / descriptors all take these)
+  // shared-space byte addresses (ld.shared / st.shared / descriptors / bulk copies all take these)
   const uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_smem = smem;                                       // [S][G][DBLK*4 atoms][8][128B]
   const uint32_t b_smem = a_smem + S * C::kAStageBytes;               // [S][G][512B]
-  const uint32_t m_smem = b_smem + S * C::kBStageBytes;               // [S][G] TileMeta
-  const uint32_t bars = m_smem + S * C::kMetaStageBytes;
-  const uint32_t meta_full = bars, full = bars + 8 * S, empty = bars + 16 * S;
-  const uint32_t acc_full = bars + 24 * S, acc_empty = acc_full + 8 * kAcc;
+  const uint32_t m_smem = b_smem + S * C::kBStageBytes;               // [MS][G] TileMeta
+  const uint32_t bars = m_smem + MS * C::kMetaStageBytes;
+  const uint32_t meta_full = bars, meta_empty = bars + 8 * MS;
+  const uint32_t full = bars + 16 * MS, empty = full + 8 * S;
+  const uint32_t acc_full = empty + 8 * S, acc_empty = acc_full + 8 * kAcc;
   const uint32_t info_smem = acc_empty + 8 * kAcc;                    // [S] open/close word per stage
   const uint32_t tmem_slot = info_smem + 4 * S;
-  uint8_t* const smem_gen = smem_raw + (smem - smem_u32(smem_raw));   // generic view (TMA destination)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -153,9 +167,12 @@ spmm_tc_kernel(PlanView pv, const float* __restrict__ x /* tf32-rounded, 16B ali
   const int32_t n_stages = (n_tiles + kG - 1) / kG;
 
   if (threadIdx.x == 0) {
+    for (int s = 0; s < MS; ++s) {
+      mbar_init(meta_full + 8 * s, 1);                // expect_tx arrive of the meta loader + the copy's bytes
+      mbar_init(meta_empty + 8 * s, kProducers + 1);  // every producer warp + the stage's builder warp have read it
+    }
     for (int s = 0; s < S; ++s) {
-      mbar_init(meta_full + 8 * s, 1);
-      mbar_init(full + 8 * s, kProducers * 32 + 1);   // every producer thread (cp.async completion) + 1 builder warp
+      mbar_init(full + 8 * s, kProducers + 1);        // one arrive per producer warp (its copies landed) + builder
       mbar_init(empty + 8 * s, 1);                    // tcgen05.commit
     }
     for (int b = 0; b < kAcc; ++b) {
@@ -173,6 +190,7 @@ spmm_tc_kernel(PlanView pv, const float* __restrict__ x /* tf32-rounded, 16B ali
   if (warp < kEpiWarps) {
     // ===================================== epilogue =====================================
     const int q = warp;  // TMEM lane quadrant == warp id % 4
+    const bool stream_y = (flags & kTuneYStream) != 0;
     for (int32_t wl = 0; wl < sl.n_windows; ++wl) {
       const int b = wl % kAcc;
       mbar_wait_backoff(acc_full + 8 * b, (wl / kAcc) & 1);
@@ -193,6 +211,7 @@ spmm_tc_kernel(PlanView pv, const float* __restrict__ x /* tf32-rounded, 16B ali
             for (int i = 0; i < 16; ++i) {
               if (row0 + i < pv.num_nodes) {
                 if (use_atomic) atomicAdd(yp + i * ldy, __uint_as_float(v[i]));
+                else if (stream_y) __stcs(yp + i * ldy, __uint_as_float(v[i]));
                 else yp[i * ldy] = __uint_as_float(v[i]);
               }
             }
@@ -205,71 +224,81 @@ spmm_tc_kernel(PlanView pv, const float* __restrict__ x /* tf32-rounded, 16B ali
     }
   } else if (warp == kMmaWarp) {
     // ===================================== MMA issuer ===================================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_tf32(128, 16, /*A MN-major*/ true, /*B K-major*/ false);
-      // A: MN-major tf32 -> SWIZZLE_128B_BASE32B atoms of 32 features x 4 k-rows (4 x 128 B): feature blocks
-      // 1024 B apart (LBO), the two k-halves of a K=8 MMA 512 B apart (SBO)
-      const uint64_t adesc0 = make_smem_desc(0, 1024, 512, kSwizzle128BBase32B);
-      // B: K-major, no swizzle: 8x16B core matrices; K chunks 128 B apart (LBO), 8-row groups 256 B apart (SBO)
-      const uint64_t bdesc0 = make_smem_desc(0, 128, 256, kSwizzleNone);
-      const bool skip_mma = (ablate & kAblateMma) != 0;
-      int32_t wl = 0;
-      uint32_t acc = tmem_base;
-      int b = 0;
-      int s = 0;
-      uint32_t ph = 0;
-      for (int32_t k = 0; k < n_stages; ++k) {
-        mbar_wait(full + 8 * s, ph);
-        fence_proxy_async_smem();   // cp.async (generic-proxy) writes of the A tiles -> tcgen05 operand reads
-        tc_fence_after();
-        const uint32_t info = lds_u32(info_smem + 4 * s);   // bits [0,G): tile opens a window, [8,8+G): closes, [16,..): tiles
-        const int nt = static_cast<int>(info >> 16);
-        uint32_t a_addr = a_smem + s * C::kAStageBytes;
-        uint32_t b_addr = b_smem + s * C::kBStageBytes;
+    // The whole warp runs the loop (warp-uniform control flow keeps addresses and descriptors in uniform
+    // registers); one elected lane issues tcgen05.mma / tcgen05.commit.  Per tile: one descriptor add, one MMA.
+    constexpr uint32_t idesc = make_idesc_tf32(128, 16, /*A MN-major*/ true, /*B K-major*/ false);
+    // A: MN-major tf32 -> SWIZZLE_128B_BASE32B atoms of 32 features x 4 k-rows (4 x 128 B): feature blocks
+    // 1024 B apart (LBO), the two k-halves of a K=8 MMA 512 B apart (SBO)
+    const uint64_t adesc0 = make_smem_desc(0, 1024, 512, kSwizzle128BBase32B);
+    // B: K-major, no swizzle: 8x16B core matrices; K chunks 128 B apart (LBO), 8-row groups 256 B apart (SBO)
+    const uint64_t bdesc0 = make_smem_desc(0, 128, 256, kSwizzleNone);
+    const bool skip_mma = (flags & kAblateMma) != 0;
+    int32_t wl = 0;        // windows opened so far
+    uint32_t acc = tmem_base;
+    int b = 0;
+    int s = 0;
+    uint32_t ph = 0;
+    for (int32_t k = 0; k < n_stages; ++k) {
+      mbar_wait(full + 8 * s, ph);   // producers / builders fenced their generic-proxy writes before arriving
+      tc_fence_after();
+      const uint32_t info = lds_u32(info_smem + 4 * s);   // bits [0,G): tile opens a window, [8,8+G): closes, [16,..): tiles
+      const int nt = static_cast<int>(info >> 16);
+      const uint64_t adesc_s = adesc0 | static_cast<uint64_t>(((a_smem + s * C::kAStageBytes) & 0x3FFFFu) >> 4);
+      const uint64_t bdesc_s = bdesc0 | static_cast<uint64_t>(((b_smem + s * C::kBStageBytes) & 0x3FFFFu) >> 4);
+      if (info == (static_cast<uint32_t>(kG) << 16) && !skip_mma) {
+        // common case in dense windows: a full stage strictly inside one window -> G back-to-back MMAs
+        if (elect_one()) {
 #pragma unroll
-        for (int j = 0; j < kG; ++j) {
-          if (j < nt) {
-            const bool first = (info >> j) & 1u;
-            if (first) {
-              b = wl % kAcc;
-              acc = tmem_base + b * DBLK * 16;
-              mbar_wait(acc_empty + 8 * b, ((wl / kAcc) & 1) ^ 1);
-              tc_fence_after();
-            }
-            if (!skip_mma || first) {
-              const uint64_t bdesc = bdesc0 | static_cast<uint64_t>((b_addr & 0x3FFFFu) >> 4);
+          for (int j = 0; j < kG; ++j) {
 #pragma unroll
-              for (int m = 0; m < DBLK; ++m) {
-                const uint64_t adesc = adesc0 | static_cast<uint64_t>(((a_addr + m * 4096) & 0x3FFFFu) >> 4);
-                umma_tf32(acc + m * 16, adesc, bdesc, idesc, first ? 0u : 1u);
-              }
-            }
-            if ((info >> (8 + j)) & 1u) {
-              umma_commit(acc_full + 8 * b);
-              ++wl;
-            }
-            a_addr += C::kATileBytes;
-            b_addr += kBTileBytes;
+            for (int m = 0; m < DBLK; ++m)
+              umma_tf32(acc + m * 16, adesc_s + static_cast<uint64_t>((j * C::kATileBytes + m * 4096) >> 4),
+                        bdesc_s + static_cast<uint64_t>((j * kBTileBytes) >> 4), idesc, 1u);
           }
         }
-        umma_commit(empty + 8 * s);
-        if (++s == S) { s = 0; ph ^= 1u; }
+      } else {
+#pragma unroll
+      for (int j = 0; j < kG; ++j) {
+        if (j < nt) {
+          const bool first = (info >> j) & 1u;
+          const bool last = (info >> (8 + j)) & 1u;
+          if (first) {
+            b = wl % kAcc;
+            acc = tmem_base + b * DBLK * 16;
+            mbar_wait(acc_empty + 8 * b, ((wl / kAcc) & 1) ^ 1);
+            tc_fence_after();
+          }
+          if (elect_one()) {
+            if (!skip_mma || first) {
+#pragma unroll
+              for (int m = 0; m < DBLK; ++m)
+                umma_tf32(acc + m * 16, adesc_s + static_cast<uint64_t>((j * C::kATileBytes + m * 4096) >> 4),
+                          bdesc_s + static_cast<uint64_t>((j * kBTileBytes) >> 4), idesc, first ? 0u : 1u);
+            }
+            if (last) umma_commit(acc_full + 8 * b);
+          }
+          if (last) ++wl;
+        }
       }
-      // the last commit must land in this CTA's shared memory before the CTA may retire
-      if (n_stages > 0) mbar_wait(empty + 8 * ((n_stages - 1) % S), ((n_stages - 1) / S) & 1);
+      }
+      if (elect_one()) umma_commit(empty + 8 * s);
+      if (++s == S) { s = 0; ph ^= 1u; }
     }
+    // the last commit must land in this CTA's shared memory before the CTA may retire
+    if (n_stages > 0) mbar_wait(empty + 8 * ((n_stages - 1) % S), ((n_stages - 1) / S) & 1);
   } else if (warp == kMetaWarp) {
     // ===================================== meta loader (TMA) ============================
     if (lane == 0) {
-      int s = 0;
-      uint32_t ph = 0;
+      const uint64_t policy = (flags & kTuneMetaFirst) ? l2_policy_evict_first() : l2_policy_evict_normal();
+      int ms = 0;
+      uint32_t mph = 0;
       for (int32_t k = 0; k < n_stages; ++k) {
-        mbar_wait(empty + 8 * s, ph ^ 1u);
+        mbar_wait(meta_empty + 8 * ms, mph ^ 1u);
         const int32_t g0 = sl.t0 + k * kG;
         const uint32_t bytes = static_cast<uint32_t>(min(kG, sl.t1 - g0)) * sizeof(TileMeta);
-        mbar_arrive_expect_tx(meta_full + 8 * s, bytes);
-        tma_bulk_g2s(smem_gen + (m_smem - smem) + s * C::kMetaStageBytes, pv.tiles + g0, bytes, meta_full + 8 * s);
-        if (++s == S) { s = 0; ph ^= 1u; }
+        mbar_arrive_expect_tx(meta_full + 8 * ms, bytes);
+        tma_bulk_g2s_hint(m_smem + ms * C::kMetaStageBytes, pv.tiles + g0, bytes, meta_full + 8 * ms, policy);
+        if (++ms == MS) { ms = 0; mph ^= 1u; }
       }
     }
   } else if (warp < kProducerWarp0) {
@@ -280,24 +309,22 @@ spmm_tc_kernel(PlanView pv, const float* __restrict__ x /* tf32-rounded, 16B ali
     const int kq = (lane >> 3) & 1;
     const int word = n >> 2;
     const int shift = (n & 3) * 8 + kq * 4;
-    const bool skip = (ablate & kAblateBuild) != 0;
+    const bool skip = (flags & kAblateBuild) != 0;
     for (int32_t k = bq; k < n_stages; k += kBuilders) {
       const int s = k % S;
-      mbar_wait(meta_full + 8 * s, (k / S) & 1);
-      const uint32_t meta = m_smem + s * C::kMetaStageBytes;
+      const int ms = k % MS;
+      mbar_wait(meta_full + 8 * ms, (k / MS) & 1);
+      const uint32_t meta = m_smem + ms * C::kMetaStageBytes;
       const int32_t g0 = sl.t0 + k * kG;
       const int nt = min(kG, sl.t1 - g0);
-      // open/close word for the MMA thread: lane j looks at tile j
-      {
-        bool first = false, last = false;
-        if (lane < nt) {
-          const uint32_t flags = lds_u32(meta + lane * 64 + 56);
-          first = (flags & kTileFirst) != 0 || (g0 + lane == sl.t0);
-          last = (flags & kTileLast) != 0 || (g0 + lane == sl.t1 - 1);
-        }
-        const uint32_t fm = __ballot_sync(0xffffffffu, first), lm = __ballot_sync(0xffffffffu, last);
-        if (lane == 0) sts_u32(info_smem + 4 * s, fm | (lm << 8) | (static_cast<uint32_t>(nt) << 16));
+      // open/close word for the MMA warp: lane j looks at tile j
+      bool first = false, last = false;
+      if (lane < nt) {
+        const uint32_t tf = lds_u32(meta + lane * 64 + 56);
+        first = (tf & kTileFirst) != 0 || (g0 + lane == sl.t0);
+        last = (tf & kTileLast) != 0 || (g0 + lane == sl.t1 - 1);
       }
+      const uint32_t fm = __ballot_sync(0xffffffffu, first), lm = __ballot_sync(0xffffffffu, last);
       float4 v[kG];
 #pragma unroll
       for (int j = 0; j < kG; ++j) {   // all loads of the stage first (weighted path: up to 4*G in flight)
@@ -322,6 +349,10 @@ spmm_tc_kernel(PlanView pv, const float* __restrict__ x /* tf32-rounded, 16B ali
           }
         }
       }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(meta_empty + 8 * ms);     // the records are in registers now
+      mbar_wait(empty + 8 * s, ((k / S) & 1) ^ 1u);        // data slot consumed by the MMAs of stage k - S
+      if (lane == 0) sts_u32(info_smem + 4 * s, fm | (lm << 8) | (static_cast<uint32_t>(nt) << 16));
 #pragma unroll
       for (int j = 0; j < kG; ++j)
         if (j < nt) sts_v4(b_smem + s * C::kBStageBytes + j * kBTileBytes + lane * 16, v[j]);
@@ -334,19 +365,31 @@ spmm_tc_kernel(PlanView pv, const float* __restrict__ x /* tf32-rounded, 16B ali
     const int p = warp - kProducerWarp0;
     const int nvec = (dim + 3) >> 2;          // 16-byte vectors per feature row in this pass
     constexpr int kVecPerLane = DBLK * 8;     // 8 rows x DBLK*32 vectors / 32 lanes
-    const bool skip = (ablate & kAblateGather) != 0;
-    int s = 0;
-    uint32_t ph = 0;
+    constexpr int kMine = kG / kProducers;    // tiles of a stage gathered by this warp
+    static_assert(kG % kProducers == 0, "tiles per stage must divide among the producer warps");
+    const bool skip = (flags & kAblateGather) != 0;
+    const uint64_t policy = (flags & kTuneXLast) ? l2_policy_evict_last() : l2_policy_evict_normal();
+    int s = 0, ms = 0;
+    uint32_t ph = 0, mph = 0;
     for (int32_t k = 0; k < n_stages; ++k) {
-      mbar_wait(meta_full + 8 * s, ph);   // implies empty[s]: the meta loader waited for it
+      mbar_wait(meta_full + 8 * ms, mph);
       const int nt = skip ? 0 : min(kG, sl.t1 - (sl.t0 + k * kG));
+      int4 c0[kMine], c1[kMine];
 #pragma unroll
-      for (int j = p; j < kG; j += kProducers) {
+      for (int u = 0; u < kMine; ++u) {
+        const uint32_t meta = m_smem + ms * C::kMetaStageBytes + (p + u * kProducers) * 64;
+        c0[u] = lds_v4(meta);                 // the 8 rows to gather (-1: padding)
+        c1[u] = lds_v4(meta + 16);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(meta_empty + 8 * ms);
+      mbar_wait(empty + 8 * s, ph ^ 1u);      // slot consumed by the MMAs of stage k - S
+#pragma unroll
+      for (int u = 0; u < kMine; ++u) {
+        const int j = p + u * kProducers;
         if (j < nt) {
-          const uint32_t meta = m_smem + s * C::kMetaStageBytes + j * 64;
           const uint32_t a_tile = a_smem + s * C::kAStageBytes + j * C::kATileBytes;
-          const int4 c0 = lds_v4(meta), c1 = lds_v4(meta + 16);   // the 8 rows to gather (-1: padding)
-          const int32_t cols[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+          const int32_t cols[8] = {c0[u].x, c0[u].y, c0[u].z, c0[u].w, c1[u].x, c1[u].y, c1[u].z, c1[u].w};
           if (nvec == DBLK * 32) {
             // full-width rows: lane -> vector `lane` (+32) of each of the 8 gathered rows
 #pragma unroll
@@ -357,15 +400,15 @@ spmm_tc_kernel(PlanView pv, const float* __restrict__ x /* tf32-rounded, 16B ali
 #pragma unroll
               for (int h = 0; h < DBLK; ++h) {
                 const int v = h * 32 + lane;
-                cp_async_16(a_tile + (v >> 3) * 1024 + sw128_base32_offset(r, v & 7), src + v * 4, bytes);
+                cp_async_16_hint(a_tile + (v >> 3) * 1024 + sw128_base32_offset(r, v & 7), src + v * 4, bytes, policy);
               }
             }
           } else {
             // narrow rows (dim < DBLK*128): (row, vector) pairs r-major over the warp
             const int items = 8 * nvec;
 #pragma unroll
-            for (int u = 0; u < kVecPerLane; ++u) {
-              const int item = u * 32 + lane;
+            for (int t = 0; t < kVecPerLane; ++t) {
+              const int item = t * 32 + lane;
               if (item < items) {
                 const int r = item / nvec;
                 const int v = item - r * nvec;
@@ -373,16 +416,30 @@ spmm_tc_kernel(PlanView pv, const float* __restrict__ x /* tf32-rounded, 16B ali
 #pragma unroll
                 for (int i = 1; i < 8; ++i) col = r == i ? cols[i] : col;
                 const float* src = x + static_cast<int64_t>(col < 0 ? 0 : col) * ldx + v * 4;
-                cp_async_16(a_tile + (v >> 3) * 1024 + sw128_base32_offset(r, v & 7), src, col < 0 ? 0u : 16u);
+                cp_async_16_hint(a_tile + (v >> 3) * 1024 + sw128_base32_offset(r, v & 7), src, col < 0 ? 0u : 16u,
+                                 policy);
               }
             }
           }
         }
       }
-      cp_async_mbar_arrive_noinc(full + 8 * s);   // fires once this thread's copies have landed
+      cp_async_commit_group();
+      if (k >= L) {
+        // the copies of stage k - L have landed: publish them (writer-side proxy fence, one arrive per warp)
+        cp_async_wait_group<L>();
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(full + 8 * ((k - L) % S));
+      }
       if (++s == S) { s = 0; ph ^= 1u; }
+      if (++ms == MS) { ms = 0; mph ^= 1u; }
     }
+    // drain: the last min(L, n_stages) stages
     cp_async_wait_all();
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0)
+      for (int32_t k = n_stages > L ? n_stages - L : 0; k < n_stages; ++k) mbar_arrive(full + 8 * (k % S));
   }
 
   // ===================================== teardown =======================================
@@ -394,10 +451,14 @@ spmm_tc_kernel(PlanView pv, const float* __restrict__ x /* tf32-rounded, 16B ali
   }
 }
 
-uint32_t ablate_flags() {
+uint32_t kernel_flags() {
   static const uint32_t flags = [] {
-    const char* e = getenv("TCGNN_ABLATE");
-    return e ? static_cast<uint32_t>(strtoul(e, nullptr, 0)) : 0u;
+    const char* a = getenv("TCGNN_ABLATE");
+    const char* t = getenv("TCGNN_TUNE");
+    const uint32_t ablate = a ? static_cast<uint32_t>(strtoul(a, nullptr, 0)) & 7u : 0u;
+    const uint32_t tune = t ? static_cast<uint32_t>(strtoul(t, nullptr, 0)) & (kTuneXLast | kTuneMetaFirst | kTuneYStream)
+                            : kTuneDefault;
+    return ablate | tune;
   }();
   return flags;
 }
@@ -417,7 +478,7 @@ cudaError_t launch_pass(const tcgnn_plan* plan, int grid, const float* xr, int64
   spmm_zero_partial_rows<<<grid, 128, 0, stream>>>(plan->view(), y, ldy, dim);
   count_launch();
   spmm_tc_kernel<DBLK><<<grid, kThreads, C::kSmemBytes, stream>>>(plan->view(), xr, ldr, wperm, y, ldy, dim,
-                                                                   ablate_flags());
+                                                                   kernel_flags());
   count_launch();
   return cudaGetLastError();
 }
