@@ -119,6 +119,14 @@ int tcgnn_debug_umma(const void* a_image, int32_t a_bytes, const void* b_image, 
                      uint64_t adesc, uint64_t bdesc, uint32_t idesc, int32_t ksteps, int32_t a_step_bytes,
                      int32_t b_step_bytes, float* d_out, int32_t ncols, void* stream);
 
+/* Issue-rate diagnostic (tools/umma_bench.py): `n_mma` back-to-back tcgen05.mma.kind::tf32 from one CTA per
+ * grid slot, rotating over n_acc accumulators (acc_stride_cols TMEM columns apart) and n_a / n_b operand
+ * tiles in zero-filled shared memory; cycles_out[0] = SM cycles until the last MMA was issued,
+ * cycles_out[1] = until the commit after it arrived (block 0).  Synchronises the stream. */
+int tcgnn_debug_umma_bench(uint64_t adesc, uint64_t bdesc, uint32_t idesc, int32_t n_mma, int32_t n_acc,
+                           int32_t acc_stride_cols, int32_t n_a, int32_t a_step_bytes, int32_t n_b,
+                           int32_t b_step_bytes, int32_t grid, int64_t cycles_out[2], void* stream);
+
 /* Number of kernels launched by the calling thread through this library since the last reset
  * (bench.py's gpu_launches). */
 int64_t tcgnn_launch_count(int reset);

@@ -165,4 +165,11 @@ int tcgnn_debug_umma(const void* a_image, int32_t a_bytes, const void* b_image, 
                     d_out, ncols, static_cast<cudaStream_t>(stream));
 }
 
+int tcgnn_debug_umma_bench(uint64_t adesc, uint64_t bdesc, uint32_t idesc, int32_t n_mma, int32_t n_acc,
+                           int32_t acc_stride_cols, int32_t n_a, int32_t a_step_bytes, int32_t n_b,
+                           int32_t b_step_bytes, int32_t grid, int64_t cycles_out[2], void* stream) {
+  return debug_umma_bench(adesc, bdesc, idesc, n_mma, n_acc, acc_stride_cols, n_a, a_step_bytes, n_b, b_step_bytes,
+                          grid, cycles_out, static_cast<cudaStream_t>(stream));
+}
+
 }  // extern "C"

@@ -78,5 +78,8 @@ int sgt_cuda(const int32_t* row_ptr, const int32_t* col_idx, int32_t num_nodes, 
 int debug_umma(const void* a_image, int32_t a_bytes, const void* b_image, int32_t b_bytes, uint64_t adesc,
                uint64_t bdesc, uint32_t idesc, int32_t ksteps, int32_t a_step_bytes, int32_t b_step_bytes,
                float* d_out, int32_t ncols, cudaStream_t stream);
+int debug_umma_bench(uint64_t adesc, uint64_t bdesc, uint32_t idesc, int32_t n_mma, int32_t n_acc, int32_t acc_stride,
+                     int32_t n_a, int32_t a_step, int32_t n_b, int32_t b_step, int32_t grid, int64_t* cycles_out,
+                     cudaStream_t stream);
 
 }  // namespace tcgnn

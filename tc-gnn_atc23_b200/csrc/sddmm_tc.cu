@@ -17,13 +17,12 @@
 //   warps 0-3  epilogue     TMEM -> registers -> masked scatter of edge values
 //   warp  4    MMA issuer   (warp-uniform loop, one elected lane issues)
 //   warp  5    meta loader  (TMA)
-//   warps 6-9  producers    cp.async (LDGSTS, zero-fill) of 128 gathered rows + the window's 16 rows,
-//                           32 features each, into the 128B-swizzled K-major images.  A thread keeps its
-//                           nine row ids in registers for all chunks of a group; every stage is one
-//                           cp.async group, and a warp publishes stage k - kLag with ONE mbarrier arrive
-//                           once cp.async.wait_group says its copies have landed (per-thread
-//                           cp.async.mbarrier arrivals -- 128 per stage -- serialise in the LSU and were the
-//                           bottleneck of the first version of this pipeline).
+//   warps 6-11 producers   warp p OWNS the stages k = p (mod 6): cp.async (LDGSTS, zero-fill) of the 128
+//                           gathered rows + the window's 16 rows, 32 features each, into the 128B-swizzled
+//                           K-major images; it publishes the stage with ONE mbarrier arrive once
+//                           cp.async.wait_group says the copies have landed (see spmm_tc.cu for the history
+//                           of this pipeline: per-thread cp.async.mbarrier arrivals and all-warps-per-stage
+//                           schemes were 2-2.5x slower).
 #include <stdlib.h>
 
 #include "plan.h"
@@ -33,13 +32,12 @@ namespace tcgnn {
 namespace {
 
 constexpr int kStages = 10;
-constexpr int kLag = 7;                                   // stages a producer keeps in flight (<= kStages - 1)
-constexpr int kMetaStages = 8;                            // ring of group records
+constexpr int kMetaStages = 16;                           // ring of group records
 constexpr int kEpiWarps = 4;
 constexpr int kMmaWarp = 4;
 constexpr int kMetaWarp = 5;
 constexpr int kProducerWarp0 = 6;
-constexpr int kProducers = 4;
+constexpr int kProducers = 6;                             // producer warp p owns the stages p, p + 6, ...
 constexpr int kWarps = kProducerWarp0 + kProducers;
 constexpr int kThreads = kWarps * 32;
 constexpr int kAcc = 4;
@@ -51,7 +49,8 @@ constexpr int kMetaStageBytes = kMetaTileBytes + 16;       // + header {tile_sta
 constexpr uint32_t kTmemCols = kAcc * 16;
 constexpr int kSmemBytes = kStages * (kAStageBytes + kBStageBytes) + kMetaStages * kMetaStageBytes +
                            (2 * kMetaStages + 2 * kStages + 2 * kAcc) * 8 + 16 + 1024;
-static_assert(kLag <= kStages - 1, "a producer must signal stage k-kLag before it needs slot k-kStages");
+static_assert(kProducers <= kStages, "a warp may not wait for the slot of an own stage it has not published yet");
+static_assert(kMetaStages >= 2 * kProducers, "one feature chunk per group: every in-flight stage is another group");
 static_assert(kSmemBytes <= 232448, "exceeds the 227 KB of dynamic shared memory per CTA");
 constexpr uint32_t kTuneXLast = 16u;                       // env TCGNN_TUNE: gathers with L2 evict_last
 
@@ -95,10 +94,10 @@ sddmm_tc_kernel(PlanView pv, const int4* __restrict__ groups, int32_t num_groups
   if (threadIdx.x == 0) {
     for (int s = 0; s < kMetaStages; ++s) {
       mbar_init(meta_full + 8 * s, 1);
-      mbar_init(meta_empty + 8 * s, kProducers);   // every producer warp has taken its row ids
+      mbar_init(meta_empty + 8 * s, nkc);          // the owners of the group's nkc stages have taken the row ids
     }
     for (int s = 0; s < kStages; ++s) {
-      mbar_init(full + 8 * s, kProducers);         // one arrive per producer warp once its copies have landed
+      mbar_init(full + 8 * s, 1);                  // the stage's producer warp, once its copies have landed
       mbar_init(empty + 8 * s, 1);                 // tcgen05.commit
     }
     for (int b = 0; b < kAcc; ++b) {
@@ -213,70 +212,64 @@ sddmm_tc_kernel(PlanView pv, const int4* __restrict__ groups, int32_t num_groups
     // ===================================== producers ====================================
     const int pw = warp - kProducerWarp0;
     constexpr int kRows = 128 + TCGNN_BLK_H;          // gathered rows + the window's own rows
-    constexpr int kItems = kRows * 8;                 // 16-byte vectors per stage
-    constexpr int kPerLane = (kItems + kProducers * 32 - 1) / (kProducers * 32);   // 9
+    constexpr int kPerLane = kRows * 8 / 32;          // 36 16-byte vectors per lane and stage
     const int nvec = (dim + 3) >> 2;                  // valid 16-byte vectors per row
     const uint64_t policy = (flags & kTuneXLast) ? l2_policy_evict_last() : l2_policy_evict_normal();
-    int s = 0, ms = 0;
-    uint32_t ph = 0, mph = 0;
-    int32_t k = 0;
-    for (int32_t gl = 0; gl < n_groups; ++gl) {
-      // this thread's rows of the group: the same (row, vector) items in every feature chunk
-      mbar_wait(meta_full + 8 * ms, mph);
+    const int v = lane & 7;                           // my vector inside the 32-feature chunk
+    const int rsub = lane >> 3;                       // my row inside each group of 4 rows
+    int32_t published = pw;                           // oldest own stage not yet published
+    int32_t gl = pw / nkc, kc = pw % nkc;
+    for (int32_t k = pw; k < n_stages; k += kProducers) {
+      const int s = k % kStages;
+      const int ms = gl % kMetaStages;
+      mbar_wait(meta_full + 8 * ms, (gl / kMetaStages) & 1);
       const uint32_t meta = m_smem + ms * kMetaStageBytes;
       const int4 hdr = lds_v4(meta + kMetaTileBytes);
       const int32_t ntiles = hdr.y, win = hdr.z;
-      int32_t node[kPerLane];
+      int32_t node[kPerLane];                         // row u*4 + rsub of the stage image
 #pragma unroll
       for (int u = 0; u < kPerLane; ++u) {
-        const int item = u * (kProducers * 32) + pw * 32 + lane;
-        const int row = item >> 3;
+        const int row = u * 4 + rsub;
         node[u] = -1;
-        if (item < kItems) {
-          if (row < 128) {
-            if ((row >> 3) < ntiles) node[u] = static_cast<int32_t>(lds_u32(meta + (row >> 3) * 64 + (row & 7) * 4));
-          } else {
-            const int32_t r = win * TCGNN_BLK_H + (row - 128);
-            node[u] = r < pv.num_nodes ? r + pv.row_base : -1;   // the window's own rows (global ids)
-          }
+        if (row < 128) {
+          if ((row >> 3) < ntiles) node[u] = static_cast<int32_t>(lds_u32(meta + (row >> 3) * 64 + (row & 7) * 4));
+        } else {
+          const int32_t r = win * TCGNN_BLK_H + (row - 128);
+          node[u] = r < pv.num_nodes ? r + pv.row_base : -1;   // the window's own rows (global ids)
         }
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(meta_empty + 8 * ms);
-      if (++ms == kMetaStages) { ms = 0; mph ^= 1u; }
-      for (int32_t kc = 0; kc < nkc; ++kc, ++k) {
-        mbar_wait(empty + 8 * s, ph ^ 1u);             // slot consumed by the MMAs of stage k - kStages
-        const uint32_t a_stage = a_smem + s * kAStageBytes;
-        const uint32_t b_stage = b_smem + s * kBStageBytes;
-#pragma unroll
-        for (int u = 0; u < kPerLane; ++u) {
-          const int item = u * (kProducers * 32) + pw * 32 + lane;
-          if (item < kItems) {
-            const int row = item >> 3, v = item & 7;
-            const int vg = kc * 8 + v;                               // vector index inside the feature row
-            const bool valid = node[u] >= 0 && vg < nvec;
-            const float* src = x + static_cast<int64_t>(valid ? node[u] : 0) * ldx + (valid ? vg * 4 : 0);
-            const uint32_t dst = row < 128 ? a_stage + (row >> 3) * 1024 + sw128_offset(row & 7, v)
-                                           : b_stage + ((row - 128) >> 3) * 1024 + sw128_offset(row & 7, v);
-            cp_async_16_hint(dst, src, valid ? 16u : 0u, policy);    // padding rows / feature tail: zero-fill
-          }
-        }
-        cp_async_commit_group();
-        if (k >= kLag) {
-          // the copies of stage k - kLag have landed: publish them (writer-side proxy fence, one arrive per warp)
-          cp_async_wait_group<kLag>();
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(full + 8 * ((k - kLag) % kStages));
-        }
-        if (++s == kStages) { s = 0; ph ^= 1u; }
+      // publish the previous own stage once its copies have landed -- BEFORE blocking on a free slot
+      if (k - published >= kProducers) {
+        cp_async_wait_group<0>();
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(full + 8 * (published % kStages));
+        published += kProducers;
       }
+      mbar_wait(empty + 8 * s, ((k / kStages) & 1) ^ 1u);    // slot consumed by the MMAs of stage k - kStages
+      const uint32_t a_stage = a_smem + s * kAStageBytes;
+      const uint32_t b_stage = b_smem + s * kBStageBytes;
+      const int vg = kc * 8 + v;                             // vector index inside the feature row
+#pragma unroll
+      for (int u = 0; u < kPerLane; ++u) {
+        const int row = u * 4 + rsub;
+        const bool valid = node[u] >= 0 && vg < nvec;
+        const float* src = x + static_cast<int64_t>(valid ? node[u] : 0) * ldx + (valid ? vg * 4 : 0);
+        const uint32_t dst = (u < 32 ? a_stage + (row >> 3) * 1024 : b_stage + ((row - 128) >> 3) * 1024) +
+                             sw128_offset(row & 7, v);
+        cp_async_16_hint(dst, src, valid ? 16u : 0u, policy);  // padding rows / feature tail: zero-fill
+      }
+      cp_async_commit_group();
+      kc += kProducers;
+      while (kc >= nkc) { kc -= nkc; ++gl; }
     }
     cp_async_wait_all();
     fence_proxy_async_smem();
     __syncwarp();
     if (lane == 0)
-      for (int32_t j = n_stages > kLag ? n_stages - kLag : 0; j < n_stages; ++j) mbar_arrive(full + 8 * (j % kStages));
+      for (; published < n_stages; published += kProducers) mbar_arrive(full + 8 * (published % kStages));
   }
 
   tc_fence_before();

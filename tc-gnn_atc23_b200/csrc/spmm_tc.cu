@@ -24,16 +24,17 @@
 //                            inside one window is G back-to-back MMAs with precomputed descriptors
 //   warp  5     meta loader  TMA bulk copies (UBLKCP, L2 evict_first) of the tile records into a 16-deep
 //                            ring that runs far ahead of the data stages
-//   warps 6-7   B builders   expand occupancy masks (or edge weights) into the K-major B tiles and
-//                            publish the stage's open/close word
-//   warps 8-11  A producers  asynchronous 128-bit gathers (cp.async / LDGSTS, zero-fill for padding,
-//                            L2 evict_last) of Xr rows straight into the swizzled (128B rows, 32B granule)
-//                            MN-major A tile.  Every stage is one cp.async group per thread; a warp
-//                            publishes stage k - kLag with ONE mbarrier arrive once cp.async.wait_group
-//                            says its copies have landed, so kLag stages (128 KB) of gathers are in flight
-//                            per SM and a stage costs 5 barrier arrivals (the first version used
-//                            per-thread cp.async.mbarrier arrivals: 128 serialised arrivals per stage were
-//                            60-70 % of the kernel time, profiles/r01b_ablations.txt).
+//   warps 6-11  producers    warp p OWNS the stages k = p (mod 6): it gathers all G tiles of the stage with
+//                            asynchronous 128-bit copies (cp.async / LDGSTS, zero-fill for padding, L2
+//                            evict_last) straight into the swizzled (128B rows, 32B granule) MN-major A
+//                            tiles, expands the occupancy masks (or edge weights) into the K-major B tiles,
+//                            writes the stage's open/close word, and publishes the stage with ONE mbarrier
+//                            arrive once cp.async.wait_group says its copies have landed.
+// History of this pipeline (profiles/r01b_ablations.txt, r01c_ablations.txt, r01d_*.txt): per-thread
+// cp.async.mbarrier arrivals (129 per stage) serialise in the LSU: 160 ns per tile.  Four producer warps that
+// all take part in every stage, publishing with a lag: 66 ns per tile, bound by the ~600-cycle serial chain
+// (barrier waits, fences, address arithmetic) each warp walks per stage.  Stage ownership puts six such chains
+// in parallel and needs 1 arrival per stage.
 // Pipeline: S data stages of G tiles (A + B), three mbarrier rings (meta_full/meta_empty, full/empty);
 // NACC TMEM accumulators with acc_full / acc_empty so the epilogue overlaps the next windows.
 // All shared-memory metadata reads are explicit ld.shared (the generic-address loads the compiler
@@ -49,17 +50,15 @@ namespace {
 constexpr int kEpiWarps = 4;
 constexpr int kMmaWarp = 4;
 constexpr int kMetaWarp = 5;
-constexpr int kBuilderWarp0 = 6;
-constexpr int kBuilders = 2;
-constexpr int kProducerWarp0 = 8;
-constexpr int kProducers = 4;         // producer warp p gathers tiles p, p+4, ... of every stage
+constexpr int kProducerWarp0 = 6;
+constexpr int kProducers = 6;         // producer warp p owns the stages p, p + 6, ...
 constexpr int kWarps = kProducerWarp0 + kProducers;
 constexpr int kThreads = kWarps * 32;
 constexpr int kAcc = 4;               // TMEM accumulator ring
 constexpr int kBTileBytes = TCGNN_BLK_H * TCGNN_BLK_W * 4;  // 512
 // ablation switches (env TCGNN_ABLATE, profiling only -- results are wrong when set): skip the row
-// gathers / the MMAs after a window's first / the B-tile construction
-constexpr uint32_t kAblateGather = 1u, kAblateMma = 2u, kAblateBuild = 4u;
+// gathers / the MMAs after a window's first / the B-tile construction / all but one MMA of a full stage
+constexpr uint32_t kAblateGather = 1u, kAblateMma = 2u, kAblateBuild = 4u, kAblateMmaFast = 8u;
 // L2 policy switches (env TCGNN_TUNE overrides the default kTuneDefault): feature-row gathers evict_last /
 // tile stream evict_first / output rows written with streaming stores
 constexpr uint32_t kTuneXLast = 16u, kTuneMetaFirst = 32u, kTuneYStream = 64u;
@@ -73,14 +72,13 @@ struct Cfg {
   static constexpr int kBStageBytes = kG * kBTileBytes;
   static constexpr int kMetaStageBytes = kG * static_cast<int>(sizeof(TileMeta));
   static constexpr int kStages = 6;                            // data ring (A + B tiles)
-  static constexpr int kLag = 4;                               // stages a producer keeps in flight (<= kStages - 1)
   static constexpr int kMetaStages = 16;                       // tile-record ring, prefetched far ahead of the data
   static constexpr uint32_t kTmemCols = kAcc * DBLK * 16;      // 64 / 128
   static constexpr int kBarBytes = (2 * kMetaStages + 2 * kStages + 2 * kAcc) * 8;
   static constexpr int kSmemBytes = kStages * (kAStageBytes + kBStageBytes) + kMetaStages * kMetaStageBytes +
                                     kBarBytes + kStages * 4 /*info words*/ + 16 + 1024 /*alignment slack*/;
-  static_assert(kLag <= kStages - 1, "a producer must be able to signal stage k-kLag before it needs slot k-kStages");
   static_assert(kSmemBytes <= 232448, "exceeds the 227 KB of dynamic shared memory per CTA");
+  static_assert(kMetaStages >= 2 * kProducers, "a producer reads the records of its next stage while the previous is in flight");
 };
 
 struct SliceInfo {
@@ -137,7 +135,8 @@ __global__ void permute_weights_kernel(const int32_t* __restrict__ eperm, const 
     out[i] = tf32_rna(w[eperm[i]]);
 }
 
-template <int DBLK>
+// OWN_LAG: own stages a producer warp keeps in flight before it publishes the oldest
+template <int DBLK, int OWN_LAG>
 __global__ void __launch_bounds__(kThreads, 1)
 spmm_tc_kernel(PlanView pv, const float* __restrict__ x /* tf32-rounded, 16B aligned */, int64_t ldx /* % 4 == 0 */,
                const float* __restrict__ wperm, float* __restrict__ y, int64_t ldy,
@@ -146,7 +145,8 @@ spmm_tc_kernel(PlanView pv, const float* __restrict__ x /* tf32-rounded, 16B ali
   constexpr int kG = C::kG;
   constexpr int S = C::kStages;
   constexpr int MS = C::kMetaStages;
-  constexpr int L = C::kLag;
+  static_assert(OWN_LAG >= 1 && OWN_LAG * kProducers <= C::kStages,
+                "a warp may not wait for the slot of an own stage it has not published yet");
   extern __shared__ uint8_t smem_raw[];
   // shared-space byte addresses (ld.shared / st.shared / descriptors / bulk copies all take these)
   const uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -169,10 +169,10 @@ spmm_tc_kernel(PlanView pv, const float* __restrict__ x /* tf32-rounded, 16B ali
   if (threadIdx.x == 0) {
     for (int s = 0; s < MS; ++s) {
       mbar_init(meta_full + 8 * s, 1);                // expect_tx arrive of the meta loader + the copy's bytes
-      mbar_init(meta_empty + 8 * s, kProducers + 1);  // every producer warp + the stage's builder warp have read it
+      mbar_init(meta_empty + 8 * s, 1);               // the stage's producer warp is done with the records
     }
     for (int s = 0; s < S; ++s) {
-      mbar_init(full + 8 * s, kProducers + 1);        // one arrive per producer warp (its copies landed) + builder
+      mbar_init(full + 8 * s, 1);                     // the stage's producer warp: copies landed, B tiles written
       mbar_init(empty + 8 * s, 1);                    // tcgen05.commit
     }
     for (int b = 0; b < kAcc; ++b) {
@@ -239,9 +239,11 @@ spmm_tc_kernel(PlanView pv, const float* __restrict__ x /* tf32-rounded, 16B ali
     int s = 0;
     uint32_t ph = 0;
     for (int32_t k = 0; k < n_stages; ++k) {
-      mbar_wait(full + 8 * s, ph);   // producers / builders fenced their generic-proxy writes before arriving
+      mbar_wait(full + 8 * s, ph);   // the producer fenced its generic-proxy writes before arriving
       tc_fence_after();
-      const uint32_t info = lds_u32(info_smem + 4 * s);   // bits [0,G): tile opens a window, [8,8+G): closes, [16,..): tiles
+      // bits [0,G): tile opens a window, [8,8+G): closes, [16,..): tiles.  The shuffle tells the compiler the
+      // word is warp-uniform, so the branches below stay uniform.
+      const uint32_t info = __shfl_sync(0xffffffffu, lds_u32(info_smem + 4 * s), 0);
       const int nt = static_cast<int>(info >> 16);
       const uint64_t adesc_s = adesc0 | static_cast<uint64_t>(((a_smem + s * C::kAStageBytes) & 0x3FFFFu) >> 4);
       const uint64_t bdesc_s = bdesc0 | static_cast<uint64_t>(((b_smem + s * C::kBStageBytes) & 0x3FFFFu) >> 4);
@@ -250,6 +252,7 @@ spmm_tc_kernel(PlanView pv, const float* __restrict__ x /* tf32-rounded, 16B ali
         if (elect_one()) {
 #pragma unroll
           for (int j = 0; j < kG; ++j) {
+            if (j > 0 && (flags & kAblateMmaFast)) break;
 #pragma unroll
             for (int m = 0; m < DBLK; ++m)
               umma_tf32(acc + m * 16, adesc_s + static_cast<uint64_t>((j * C::kATileBytes + m * 4096) >> 4),
@@ -258,28 +261,28 @@ spmm_tc_kernel(PlanView pv, const float* __restrict__ x /* tf32-rounded, 16B ali
         }
       } else {
 #pragma unroll
-      for (int j = 0; j < kG; ++j) {
-        if (j < nt) {
-          const bool first = (info >> j) & 1u;
-          const bool last = (info >> (8 + j)) & 1u;
-          if (first) {
-            b = wl % kAcc;
-            acc = tmem_base + b * DBLK * 16;
-            mbar_wait(acc_empty + 8 * b, ((wl / kAcc) & 1) ^ 1);
-            tc_fence_after();
-          }
-          if (elect_one()) {
-            if (!skip_mma || first) {
-#pragma unroll
-              for (int m = 0; m < DBLK; ++m)
-                umma_tf32(acc + m * 16, adesc_s + static_cast<uint64_t>((j * C::kATileBytes + m * 4096) >> 4),
-                          bdesc_s + static_cast<uint64_t>((j * kBTileBytes) >> 4), idesc, first ? 0u : 1u);
+        for (int j = 0; j < kG; ++j) {
+          if (j < nt) {
+            const bool first = (info >> j) & 1u;
+            const bool last = (info >> (8 + j)) & 1u;
+            if (first) {
+              b = wl % kAcc;
+              acc = tmem_base + b * DBLK * 16;
+              mbar_wait(acc_empty + 8 * b, ((wl / kAcc) & 1) ^ 1);
+              tc_fence_after();
             }
-            if (last) umma_commit(acc_full + 8 * b);
+            if (elect_one()) {
+              if (!skip_mma || first) {
+#pragma unroll
+                for (int m = 0; m < DBLK; ++m)
+                  umma_tf32(acc + m * 16, adesc_s + static_cast<uint64_t>((j * C::kATileBytes + m * 4096) >> 4),
+                            bdesc_s + static_cast<uint64_t>((j * kBTileBytes) >> 4), idesc, first ? 0u : 1u);
+              }
+              if (last) umma_commit(acc_full + 8 * b);
+            }
+            if (last) ++wl;
           }
-          if (last) ++wl;
         }
-      }
       }
       if (elect_one()) umma_commit(empty + 8 * s);
       if (++s == S) { s = 0; ph ^= 1u; }
@@ -301,22 +304,51 @@ spmm_tc_kernel(PlanView pv, const float* __restrict__ x /* tf32-rounded, 16B ali
         if (++ms == MS) { ms = 0; mph ^= 1u; }
       }
     }
-  } else if (warp < kProducerWarp0) {
-    // ===================================== B builders ===================================
-    const int bq = warp - kBuilderWarp0;
-    // lane -> 16-byte chunk `lane` of the tile: [n/8][k/4][n%8] x 4 floats (k%4)
-    const int n = (lane >> 4) * 8 + (lane & 7);
-    const int kq = (lane >> 3) & 1;
-    const int word = n >> 2;
-    const int shift = (n & 3) * 8 + kq * 4;
-    const bool skip = (flags & kAblateBuild) != 0;
-    for (int32_t k = bq; k < n_stages; k += kBuilders) {
+  } else {
+    // ===================================== producers ====================================
+    const int p = warp - kProducerWarp0;
+    const int nvec = (dim + 3) >> 2;          // 16-byte vectors per feature row in this pass
+    constexpr int kVecPerLane = DBLK * 8;     // 8 rows x DBLK*32 vectors / 32 lanes
+    const bool skip_gather = (flags & kAblateGather) != 0;
+    const bool skip_build = (flags & kAblateBuild) != 0;
+    const uint64_t policy = (flags & kTuneXLast) ? l2_policy_evict_last() : l2_policy_evict_normal();
+    // B tile: lane -> 16-byte chunk `lane` of the tile: [n/8][k/4][n%8] x 4 floats (k%4)
+    const int bn = (lane >> 4) * 8 + (lane & 7);
+    const int bword = bn >> 2;
+    const int bshift = (bn & 3) * 8 + ((lane >> 3) & 1) * 4;
+    int32_t published = p;                    // oldest own stage not yet published
+    for (int32_t k = p; k < n_stages; k += kProducers) {
       const int s = k % S;
       const int ms = k % MS;
-      mbar_wait(meta_full + 8 * ms, (k / MS) & 1);
-      const uint32_t meta = m_smem + ms * C::kMetaStageBytes;
       const int32_t g0 = sl.t0 + k * kG;
       const int nt = min(kG, sl.t1 - g0);
+      mbar_wait(meta_full + 8 * ms, (k / MS) & 1);
+      const uint32_t meta = m_smem + ms * C::kMetaStageBytes;
+      // B values of the stage (weighted: global loads, issued first so they overlap everything below)
+      float4 bv[kG];
+#pragma unroll
+      for (int j = 0; j < kG; ++j) {
+        bv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (j < nt && !skip_build) {
+          const uint32_t mw = lds_u32(meta + j * 64 + 32 + bword * 4);
+          const uint32_t nib = (mw >> bshift) & 0xFu;
+          if (wperm == nullptr) {
+            bv[j].x = (nib & 1u) ? 1.0f : 0.0f;
+            bv[j].y = (nib & 2u) ? 1.0f : 0.0f;
+            bv[j].z = (nib & 4u) ? 1.0f : 0.0f;
+            bv[j].w = (nib & 8u) ? 1.0f : 0.0f;
+          } else if (nib != 0u) {
+            // rank of the first of my four bits among the tile's set bits (bit order r*8+c)
+            int rank = __popc(mw & ((1u << bshift) - 1u));
+            for (int i = 0; i < bword; ++i) rank += __popc(lds_u32(meta + j * 64 + 32 + i * 4));
+            const float* wp = wperm + static_cast<int32_t>(lds_u32(meta + j * 64 + 52)) + rank;
+            if (nib & 1u) bv[j].x = __ldg(wp++);
+            if (nib & 2u) bv[j].y = __ldg(wp++);
+            if (nib & 4u) bv[j].z = __ldg(wp++);
+            if (nib & 8u) bv[j].w = __ldg(wp++);
+          }
+        }
+      }
       // open/close word for the MMA warp: lane j looks at tile j
       bool first = false, last = false;
       if (lane < nt) {
@@ -325,121 +357,73 @@ spmm_tc_kernel(PlanView pv, const float* __restrict__ x /* tf32-rounded, 16B ali
         last = (tf & kTileLast) != 0 || (g0 + lane == sl.t1 - 1);
       }
       const uint32_t fm = __ballot_sync(0xffffffffu, first), lm = __ballot_sync(0xffffffffu, last);
-      float4 v[kG];
-#pragma unroll
-      for (int j = 0; j < kG; ++j) {   // all loads of the stage first (weighted path: up to 4*G in flight)
-        v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (j < nt && !skip) {
-          const uint32_t mw = lds_u32(meta + j * 64 + 32 + word * 4);
-          const uint32_t nib = (mw >> shift) & 0xFu;
-          if (wperm == nullptr) {
-            v[j].x = (nib & 1u) ? 1.0f : 0.0f;
-            v[j].y = (nib & 2u) ? 1.0f : 0.0f;
-            v[j].z = (nib & 4u) ? 1.0f : 0.0f;
-            v[j].w = (nib & 8u) ? 1.0f : 0.0f;
-          } else if (nib != 0u) {
-            // rank of the first of my four bits among the tile's set bits (bit order r*8+c)
-            int rank = __popc(mw & ((1u << shift) - 1u));
-            for (int i = 0; i < word; ++i) rank += __popc(lds_u32(meta + j * 64 + 32 + i * 4));
-            const float* wp = wperm + static_cast<int32_t>(lds_u32(meta + j * 64 + 52)) + rank;
-            if (nib & 1u) v[j].x = __ldg(wp++);
-            if (nib & 2u) v[j].y = __ldg(wp++);
-            if (nib & 4u) v[j].z = __ldg(wp++);
-            if (nib & 8u) v[j].w = __ldg(wp++);
-          }
-        }
+      // publish the oldest own stage once its copies have landed -- BEFORE blocking on a free slot, so a
+      // landed stage never waits for the MMAs of an older one
+      if (k - published >= OWN_LAG * kProducers) {
+        cp_async_wait_group<OWN_LAG - 1>();
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(full + 8 * (published % S));
+        published += kProducers;
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(meta_empty + 8 * ms);     // the records are in registers now
-      mbar_wait(empty + 8 * s, ((k / S) & 1) ^ 1u);        // data slot consumed by the MMAs of stage k - S
-      if (lane == 0) sts_u32(info_smem + 4 * s, fm | (lm << 8) | (static_cast<uint32_t>(nt) << 16));
+      mbar_wait(empty + 8 * s, ((k / S) & 1) ^ 1u);   // slot consumed by the MMAs of stage k - S
+      if (!skip_gather) {
+#pragma unroll 2
+        for (int j = 0; j < kG; ++j) {
+          if (j < nt) {
+            const uint32_t a_tile = a_smem + s * C::kAStageBytes + j * C::kATileBytes;
+            const int4 c0 = lds_v4(meta + j * 64), c1 = lds_v4(meta + j * 64 + 16);   // rows to gather (-1: padding)
+            const int32_t cols[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+            if (nvec == DBLK * 32) {
+              // full-width rows: lane -> vector `lane` (+32) of each of the 8 gathered rows
 #pragma unroll
-      for (int j = 0; j < kG; ++j)
-        if (j < nt) sts_v4(b_smem + s * C::kBStageBytes + j * kBTileBytes + lane * 16, v[j]);
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(full + 8 * s);
-    }
-  } else {
-    // ===================================== A producers ==================================
-    const int p = warp - kProducerWarp0;
-    const int nvec = (dim + 3) >> 2;          // 16-byte vectors per feature row in this pass
-    constexpr int kVecPerLane = DBLK * 8;     // 8 rows x DBLK*32 vectors / 32 lanes
-    constexpr int kMine = kG / kProducers;    // tiles of a stage gathered by this warp
-    static_assert(kG % kProducers == 0, "tiles per stage must divide among the producer warps");
-    const bool skip = (flags & kAblateGather) != 0;
-    const uint64_t policy = (flags & kTuneXLast) ? l2_policy_evict_last() : l2_policy_evict_normal();
-    int s = 0, ms = 0;
-    uint32_t ph = 0, mph = 0;
-    for (int32_t k = 0; k < n_stages; ++k) {
-      mbar_wait(meta_full + 8 * ms, mph);
-      const int nt = skip ? 0 : min(kG, sl.t1 - (sl.t0 + k * kG));
-      int4 c0[kMine], c1[kMine];
+              for (int r = 0; r < 8; ++r) {
+                const int32_t col = cols[r];
+                const float* src = x + static_cast<int64_t>(col < 0 ? 0 : col) * ldx;
+                const uint32_t bytes = col < 0 ? 0u : 16u;   // padding column: zero-fill
 #pragma unroll
-      for (int u = 0; u < kMine; ++u) {
-        const uint32_t meta = m_smem + ms * C::kMetaStageBytes + (p + u * kProducers) * 64;
-        c0[u] = lds_v4(meta);                 // the 8 rows to gather (-1: padding)
-        c1[u] = lds_v4(meta + 16);
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(meta_empty + 8 * ms);
-      mbar_wait(empty + 8 * s, ph ^ 1u);      // slot consumed by the MMAs of stage k - S
-#pragma unroll
-      for (int u = 0; u < kMine; ++u) {
-        const int j = p + u * kProducers;
-        if (j < nt) {
-          const uint32_t a_tile = a_smem + s * C::kAStageBytes + j * C::kATileBytes;
-          const int32_t cols[8] = {c0[u].x, c0[u].y, c0[u].z, c0[u].w, c1[u].x, c1[u].y, c1[u].z, c1[u].w};
-          if (nvec == DBLK * 32) {
-            // full-width rows: lane -> vector `lane` (+32) of each of the 8 gathered rows
-#pragma unroll
-            for (int r = 0; r < 8; ++r) {
-              const int32_t col = cols[r];
-              const float* src = x + static_cast<int64_t>(col < 0 ? 0 : col) * ldx;
-              const uint32_t bytes = col < 0 ? 0u : 16u;   // padding column: zero-fill
-#pragma unroll
-              for (int h = 0; h < DBLK; ++h) {
-                const int v = h * 32 + lane;
-                cp_async_16_hint(a_tile + (v >> 3) * 1024 + sw128_base32_offset(r, v & 7), src + v * 4, bytes, policy);
+                for (int h = 0; h < DBLK; ++h) {
+                  const int v = h * 32 + lane;
+                  cp_async_16_hint(a_tile + (v >> 3) * 1024 + sw128_base32_offset(r, v & 7), src + v * 4, bytes, policy);
+                }
               }
-            }
-          } else {
-            // narrow rows (dim < DBLK*128): (row, vector) pairs r-major over the warp
-            const int items = 8 * nvec;
+            } else {
+              // narrow rows (dim < DBLK*128): (row, vector) pairs r-major over the warp
+              const int items = 8 * nvec;
 #pragma unroll
-            for (int t = 0; t < kVecPerLane; ++t) {
-              const int item = t * 32 + lane;
-              if (item < items) {
-                const int r = item / nvec;
-                const int v = item - r * nvec;
-                int32_t col = cols[0];
+              for (int t = 0; t < kVecPerLane; ++t) {
+                const int item = t * 32 + lane;
+                if (item < items) {
+                  const int r = item / nvec;
+                  const int v = item - r * nvec;
+                  int32_t col = cols[0];
 #pragma unroll
-                for (int i = 1; i < 8; ++i) col = r == i ? cols[i] : col;
-                const float* src = x + static_cast<int64_t>(col < 0 ? 0 : col) * ldx + v * 4;
-                cp_async_16_hint(a_tile + (v >> 3) * 1024 + sw128_base32_offset(r, v & 7), src, col < 0 ? 0u : 16u,
-                                 policy);
+                  for (int i = 1; i < 8; ++i) col = r == i ? cols[i] : col;
+                  const float* src = x + static_cast<int64_t>(col < 0 ? 0 : col) * ldx + v * 4;
+                  cp_async_16_hint(a_tile + (v >> 3) * 1024 + sw128_base32_offset(r, v & 7), src, col < 0 ? 0u : 16u,
+                                   policy);
+                }
               }
             }
           }
         }
       }
       cp_async_commit_group();
-      if (k >= L) {
-        // the copies of stage k - L have landed: publish them (writer-side proxy fence, one arrive per warp)
-        cp_async_wait_group<L>();
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(full + 8 * ((k - L) % S));
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(meta_empty + 8 * ms);             // every lane has read the records
+        sts_u32(info_smem + 4 * s, fm | (lm << 8) | (static_cast<uint32_t>(nt) << 16));
       }
-      if (++s == S) { s = 0; ph ^= 1u; }
-      if (++ms == MS) { ms = 0; mph ^= 1u; }
+#pragma unroll
+      for (int j = 0; j < kG; ++j)
+        if (j < nt) sts_v4(b_smem + s * C::kBStageBytes + j * kBTileBytes + lane * 16, bv[j]);
     }
-    // drain: the last min(L, n_stages) stages
+    // drain: publish the own stages still in flight
     cp_async_wait_all();
     fence_proxy_async_smem();
     __syncwarp();
     if (lane == 0)
-      for (int32_t k = n_stages > L ? n_stages - L : 0; k < n_stages; ++k) mbar_arrive(full + 8 * (k % S));
+      for (; published < n_stages; published += kProducers) mbar_arrive(full + 8 * (published % S));
   }
 
   // ===================================== teardown =======================================
@@ -455,7 +439,7 @@ uint32_t kernel_flags() {
   static const uint32_t flags = [] {
     const char* a = getenv("TCGNN_ABLATE");
     const char* t = getenv("TCGNN_TUNE");
-    const uint32_t ablate = a ? static_cast<uint32_t>(strtoul(a, nullptr, 0)) & 7u : 0u;
+    const uint32_t ablate = a ? static_cast<uint32_t>(strtoul(a, nullptr, 0)) & 15u : 0u;
     const uint32_t tune = t ? static_cast<uint32_t>(strtoul(t, nullptr, 0)) & (kTuneXLast | kTuneMetaFirst | kTuneYStream)
                             : kTuneDefault;
     return ablate | tune;
@@ -463,24 +447,30 @@ uint32_t kernel_flags() {
   return flags;
 }
 
-template <int DBLK>
-cudaError_t launch_pass(const tcgnn_plan* plan, int grid, const float* xr, int64_t ldr, const float* wperm, float* y,
-                        int64_t ldy, int32_t dim, cudaStream_t stream) {
+template <int DBLK, int OWN_LAG>
+cudaError_t launch_kernel(const tcgnn_plan* plan, int grid, const float* xr, int64_t ldr, const float* wperm, float* y,
+                          int64_t ldy, int32_t dim, cudaStream_t stream) {
   using C = Cfg<DBLK>;
   static bool attr_set[64] = {};
   const int dev = plan->device;
   if (dev < 64 && !attr_set[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(spmm_tc_kernel<DBLK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(spmm_tc_kernel<DBLK, OWN_LAG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          C::kSmemBytes);
     if (e != cudaSuccess) return e;
     attr_set[dev] = true;
   }
-  spmm_zero_partial_rows<<<grid, 128, 0, stream>>>(plan->view(), y, ldy, dim);
-  count_launch();
-  spmm_tc_kernel<DBLK><<<grid, kThreads, C::kSmemBytes, stream>>>(plan->view(), xr, ldr, wperm, y, ldy, dim,
-                                                                   kernel_flags());
+  spmm_tc_kernel<DBLK, OWN_LAG><<<grid, kThreads, C::kSmemBytes, stream>>>(plan->view(), xr, ldr, wperm, y, ldy, dim,
+                                                                            kernel_flags());
   count_launch();
   return cudaGetLastError();
+}
+
+template <int DBLK>
+cudaError_t launch_pass(const tcgnn_plan* plan, int grid, const float* xr, int64_t ldr, const float* wperm, float* y,
+                        int64_t ldy, int32_t dim, cudaStream_t stream) {
+  spmm_zero_partial_rows<<<grid, 128, 0, stream>>>(plan->view(), y, ldy, dim);
+  count_launch();
+  return launch_kernel<DBLK, 1>(plan, grid, xr, ldr, wperm, y, ldy, dim, stream);
 }
 
 }  // namespace

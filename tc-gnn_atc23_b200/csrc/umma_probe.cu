@@ -65,7 +65,107 @@ umma_probe_kernel(const uint8_t* __restrict__ a_img, int a_bytes, const uint8_t*
   }
 }
 
+// Throughput probe: `n_mma` back-to-back MMAs from one elected lane, rotating over `n_acc` accumulators
+// (acc_stride TMEM columns apart) and over `n_a` / `n_b` operand tiles (a_step / b_step bytes apart).
+// Shared memory holds zeros (the result is irrelevant).  out[0] = cycles until the last MMA was issued,
+// out[1] = cycles until the commit after the last MMA arrived.
+__global__ void __launch_bounds__(128, 1)
+umma_bench_kernel(uint64_t adesc, uint64_t bdesc, uint32_t idesc, int n_mma, int n_acc, int acc_stride, int n_a,
+                  int a_step, int n_b, int b_step, long long* __restrict__ out) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t done_bar;
+  __shared__ uint32_t tmem_slot;
+  const int warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < (kProbeMaxA + kProbeMaxB) / 16; i += blockDim.x)
+    reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  if (threadIdx.x == 0) {
+    mbar_init(&done_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc<512>(&tmem_slot);
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+  if (warp == 0) {
+    const uint32_t a_addr = smem_u32(smem), b_addr = smem_u32(smem + kProbeMaxA);
+    const uint64_t ad0 = adesc + static_cast<uint64_t>((a_addr & 0x3FFFFu) >> 4);
+    const uint64_t bd0 = bdesc + static_cast<uint64_t>((b_addr & 0x3FFFFu) >> 4);
+    const long long t0 = clock64();
+    if (n_acc == 0) {
+      // production pattern: groups of 8 MMAs with compile-time operand offsets (4 KB A tiles, 512 B B tiles)
+      for (int i = 0; i < n_mma; i += 8) {
+        if (elect_one()) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            umma_tf32(tmem_base, ad0 + static_cast<uint64_t>((j * 4096) >> 4), bd0 + static_cast<uint64_t>((j * 512) >> 4),
+                      idesc, 1u);
+        }
+      }
+    } else {
+      int ia = 0, ib = 0, ic = 0;
+      for (int i = 0; i < n_mma; ++i) {
+        if (elect_one())
+          umma_tf32(tmem_base + ic * acc_stride, ad0 + static_cast<uint64_t>((ia * a_step) >> 4),
+                    bd0 + static_cast<uint64_t>((ib * b_step) >> 4), idesc, 1u);
+        if (++ia == n_a) ia = 0;
+        if (++ib == n_b) ib = 0;
+        if (++ic == n_acc) ic = 0;
+      }
+    }
+    const long long t1 = clock64();
+    if (elect_one()) umma_commit(&done_bar);
+    mbar_wait(&done_bar, 0);
+    const long long t2 = clock64();
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+      out[0] = t1 - t0;
+      out[1] = t2 - t0;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
 }  // namespace
+
+int debug_umma_bench(uint64_t adesc, uint64_t bdesc, uint32_t idesc, int32_t n_mma, int32_t n_acc, int32_t acc_stride,
+                     int32_t n_a, int32_t a_step, int32_t n_b, int32_t b_step, int32_t grid, int64_t* cycles_out,
+                     cudaStream_t stream) {
+  if (cycles_out == nullptr || n_mma < 1 || n_acc < 0 || n_a < 1 || n_b < 1 || grid < 1 ||
+      static_cast<int64_t>(n_acc) * acc_stride > 512 || static_cast<int64_t>(n_a) * a_step > kProbeMaxA ||
+      static_cast<int64_t>(n_b) * b_step > kProbeMaxB) {
+    set_last_error("tcgnn_debug_umma_bench: bad argument");
+    return TCGNN_ERR_INVALID_ARG;
+  }
+  long long* d = nullptr;
+  long long h[2] = {0, 0};
+  const int smem_bytes = kProbeMaxA + kProbeMaxB + 1024;
+  cudaError_t e = cudaMalloc(&d, sizeof(h));
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(umma_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+  if (e == cudaSuccess) {
+    umma_bench_kernel<<<grid, 128, smem_bytes, stream>>>(adesc, bdesc, idesc, n_mma, n_acc, acc_stride, n_a, a_step,
+                                                         n_b, b_step, d);
+    count_launch();
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpyAsync(h, d, sizeof(h), cudaMemcpyDeviceToHost, stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+  if (d) cudaFree(d);
+  if (e != cudaSuccess) {
+    set_last_error("tcgnn_debug_umma_bench: %s", cudaGetErrorString(e));
+    return TCGNN_ERR_CUDA;
+  }
+  cycles_out[0] = h[0];
+  cycles_out[1] = h[1];
+  return TCGNN_OK;
+}
 
 int debug_umma(const void* a_image, int32_t a_bytes, const void* b_image, int32_t b_bytes, uint64_t adesc,
                uint64_t bdesc, uint32_t idesc, int32_t ksteps, int32_t a_step_bytes, int32_t b_step_bytes,
