@@ -39,6 +39,7 @@
 // NACC TMEM accumulators with acc_full / acc_empty so the epilogue overlaps the next windows.
 // All shared-memory metadata reads are explicit ld.shared (the generic-address loads the compiler
 // emits for a runtime-aligned dynamic smem base cost the MMA thread ~300 cycles per tile).
+#include <stdio.h>
 #include <stdlib.h>
 
 #include "plan.h"
@@ -50,10 +51,7 @@ namespace {
 constexpr int kEpiWarps = 4;
 constexpr int kMmaWarp = 4;
 constexpr int kMetaWarp = 5;
-constexpr int kProducerWarp0 = 6;
-constexpr int kProducers = 6;         // producer warp p owns the stages p, p + 6, ...
-constexpr int kWarps = kProducerWarp0 + kProducers;
-constexpr int kThreads = kWarps * 32;
+constexpr int kProducerWarp0 = 6;     // producer warp p owns the stages p, p + P, ...
 constexpr int kAcc = 4;               // TMEM accumulator ring
 constexpr int kBTileBytes = TCGNN_BLK_H * TCGNN_BLK_W * 4;  // 512
 // ablation switches (env TCGNN_ABLATE, profiling only -- results are wrong when set): skip the row
@@ -64,21 +62,28 @@ constexpr uint32_t kAblateGather = 1u, kAblateMma = 2u, kAblateBuild = 4u, kAbla
 constexpr uint32_t kTuneXLast = 16u, kTuneMetaFirst = 32u, kTuneYStream = 64u;
 constexpr uint32_t kTuneDefault = kTuneXLast | kTuneMetaFirst | kTuneYStream;
 
-template <int DBLK>
+// DBLK: 128-feature blocks per pass; G: tiles per pipeline stage; S: data stages; P: producer warps;
+// L: own stages a producer warp keeps in flight before it publishes the oldest
+template <int DBLK, int G, int S_, int P, int L>
 struct Cfg {
-  static constexpr int kG = DBLK == 1 ? 8 : 4;                 // tiles per pipeline stage (32 KB of A)
+  static constexpr int kG = G;
   static constexpr int kATileBytes = DBLK * 4096;              // DBLK*4 swizzle atoms of 8 rows x 128 B
   static constexpr int kAStageBytes = kG * kATileBytes;
   static constexpr int kBStageBytes = kG * kBTileBytes;
   static constexpr int kMetaStageBytes = kG * static_cast<int>(sizeof(TileMeta));
-  static constexpr int kStages = 6;                            // data ring (A + B tiles)
+  static constexpr int kStages = S_;                           // data ring (A + B tiles)
+  static constexpr int kProducers = P;
+  static constexpr int kOwnLag = L;
+  static constexpr int kThreads = (kProducerWarp0 + P) * 32;
   static constexpr int kMetaStages = 16;                       // tile-record ring, prefetched far ahead of the data
   static constexpr uint32_t kTmemCols = kAcc * DBLK * 16;      // 64 / 128
   static constexpr int kBarBytes = (2 * kMetaStages + 2 * kStages + 2 * kAcc) * 8;
   static constexpr int kSmemBytes = kStages * (kAStageBytes + kBStageBytes) + kMetaStages * kMetaStageBytes +
                                     kBarBytes + kStages * 4 /*info words*/ + 16 + 1024 /*alignment slack*/;
+  static_assert(kG >= 1 && kG <= 8, "the open/close word holds 8 tile bits");
   static_assert(kSmemBytes <= 232448, "exceeds the 227 KB of dynamic shared memory per CTA");
-  static_assert(kMetaStages >= 2 * kProducers, "a producer reads the records of its next stage while the previous is in flight");
+  static_assert(kMetaStages >= (L + 1) * P || kMetaStages >= 16, "records of every in-flight own stage stay resident");
+  static_assert(L >= 1 && (L - 1) * P < S_, "a warp may not wait for the slot of an own stage it has not published yet");
 };
 
 struct SliceInfo {
@@ -135,18 +140,24 @@ __global__ void permute_weights_kernel(const int32_t* __restrict__ eperm, const 
     out[i] = tf32_rna(w[eperm[i]]);
 }
 
-// OWN_LAG: own stages a producer warp keeps in flight before it publishes the oldest
-template <int DBLK, int OWN_LAG>
-__global__ void __launch_bounds__(kThreads, 1)
+// Timeline probe (env TCGNN_TRACE=1, tools/trace.py): block 0 records clock64 at fixed points of the first
+// kTraceStages stages -- role 0 = MMA warp, 1 = producer warp 0, 2 = meta loader; 8 points per stage.
+constexpr int kTraceStages = 512;
+__device__ __forceinline__ void trace_put(long long* trace, int role, int32_t k, int point) {
+  if (k < kTraceStages && (threadIdx.x & 31) == 0) trace[(role * kTraceStages + k) * 8 + point] = clock64();
+}
+
+template <class C, int DBLK>
+__global__ void __launch_bounds__(C::kThreads, 1)
 spmm_tc_kernel(PlanView pv, const float* __restrict__ x /* tf32-rounded, 16B aligned */, int64_t ldx /* % 4 == 0 */,
                const float* __restrict__ wperm, float* __restrict__ y, int64_t ldy,
-               int32_t dim /* <= DBLK*128, features of this pass */, uint32_t flags /* kAblate* | kTune* bits */) {
-  using C = Cfg<DBLK>;
+               int32_t dim /* <= DBLK*128, features of this pass */, uint32_t flags /* kAblate* | kTune* bits */,
+               long long* __restrict__ trace /* nullable */) {
   constexpr int kG = C::kG;
   constexpr int S = C::kStages;
   constexpr int MS = C::kMetaStages;
-  static_assert(OWN_LAG >= 1 && OWN_LAG * kProducers <= C::kStages,
-                "a warp may not wait for the slot of an own stage it has not published yet");
+  constexpr int kProducers = C::kProducers;
+  constexpr int OWN_LAG = C::kOwnLag;
   extern __shared__ uint8_t smem_raw[];
   // shared-space byte addresses (ld.shared / st.shared / descriptors / bulk copies all take these)
   const uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -165,6 +176,7 @@ spmm_tc_kernel(PlanView pv, const float* __restrict__ x /* tf32-rounded, 16B ali
   const SliceInfo sl = slice_info(pv);
   const int32_t n_tiles = sl.t1 - sl.t0;
   const int32_t n_stages = (n_tiles + kG - 1) / kG;
+  const bool tr = trace != nullptr && blockIdx.x == 0;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < MS; ++s) {
@@ -241,12 +253,14 @@ spmm_tc_kernel(PlanView pv, const float* __restrict__ x /* tf32-rounded, 16B ali
     for (int32_t k = 0; k < n_stages; ++k) {
       mbar_wait(full + 8 * s, ph);   // the producer fenced its generic-proxy writes before arriving
       tc_fence_after();
+      if (tr) trace_put(trace, 0, k, 0);
       // bits [0,G): tile opens a window, [8,8+G): closes, [16,..): tiles.  The shuffle tells the compiler the
       // word is warp-uniform, so the branches below stay uniform.
       const uint32_t info = __shfl_sync(0xffffffffu, lds_u32(info_smem + 4 * s), 0);
       const int nt = static_cast<int>(info >> 16);
       const uint64_t adesc_s = adesc0 | static_cast<uint64_t>(((a_smem + s * C::kAStageBytes) & 0x3FFFFu) >> 4);
       const uint64_t bdesc_s = bdesc0 | static_cast<uint64_t>(((b_smem + s * C::kBStageBytes) & 0x3FFFFu) >> 4);
+      if (tr) trace_put(trace, 0, k, 1);
       if (info == (static_cast<uint32_t>(kG) << 16) && !skip_mma) {
         // common case in dense windows: a full stage strictly inside one window -> G back-to-back MMAs
         if (elect_one()) {
@@ -284,7 +298,9 @@ spmm_tc_kernel(PlanView pv, const float* __restrict__ x /* tf32-rounded, 16B ali
           }
         }
       }
+      if (tr) trace_put(trace, 0, k, 2);
       if (elect_one()) umma_commit(empty + 8 * s);
+      if (tr) trace_put(trace, 0, k, 3);
       if (++s == S) { s = 0; ph ^= 1u; }
     }
     // the last commit must land in this CTA's shared memory before the CTA may retire
@@ -296,11 +312,14 @@ spmm_tc_kernel(PlanView pv, const float* __restrict__ x /* tf32-rounded, 16B ali
       int ms = 0;
       uint32_t mph = 0;
       for (int32_t k = 0; k < n_stages; ++k) {
+        if (tr) trace_put(trace, 2, k, 0);
         mbar_wait(meta_empty + 8 * ms, mph ^ 1u);
+        if (tr) trace_put(trace, 2, k, 1);
         const int32_t g0 = sl.t0 + k * kG;
         const uint32_t bytes = static_cast<uint32_t>(min(kG, sl.t1 - g0)) * sizeof(TileMeta);
         mbar_arrive_expect_tx(meta_full + 8 * ms, bytes);
         tma_bulk_g2s_hint(m_smem + ms * C::kMetaStageBytes, pv.tiles + g0, bytes, meta_full + 8 * ms, policy);
+        if (tr) trace_put(trace, 2, k, 2);
         if (++ms == MS) { ms = 0; mph ^= 1u; }
       }
     }
@@ -322,7 +341,10 @@ spmm_tc_kernel(PlanView pv, const float* __restrict__ x /* tf32-rounded, 16B ali
       const int ms = k % MS;
       const int32_t g0 = sl.t0 + k * kG;
       const int nt = min(kG, sl.t1 - g0);
+      const bool trp = tr && p == 0;
+      if (trp) trace_put(trace, 1, k / kProducers, 0);
       mbar_wait(meta_full + 8 * ms, (k / MS) & 1);
+      if (trp) trace_put(trace, 1, k / kProducers, 1);
       const uint32_t meta = m_smem + ms * C::kMetaStageBytes;
       // B values of the stage (weighted: global loads, issued first so they overlap everything below)
       float4 bv[kG];
@@ -359,14 +381,18 @@ spmm_tc_kernel(PlanView pv, const float* __restrict__ x /* tf32-rounded, 16B ali
       const uint32_t fm = __ballot_sync(0xffffffffu, first), lm = __ballot_sync(0xffffffffu, last);
       // publish the oldest own stage once its copies have landed -- BEFORE blocking on a free slot, so a
       // landed stage never waits for the MMAs of an older one
+      if (trp) trace_put(trace, 1, k / kProducers, 2);
       if (k - published >= OWN_LAG * kProducers) {
         cp_async_wait_group<OWN_LAG - 1>();
+        if (trp) trace_put(trace, 1, k / kProducers, 3);
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(full + 8 * (published % S));
         published += kProducers;
       }
+      if (trp) trace_put(trace, 1, k / kProducers, 4);
       mbar_wait(empty + 8 * s, ((k / S) & 1) ^ 1u);   // slot consumed by the MMAs of stage k - S
+      if (trp) trace_put(trace, 1, k / kProducers, 5);
       if (!skip_gather) {
 #pragma unroll 2
         for (int j = 0; j < kG; ++j) {
@@ -409,6 +435,7 @@ spmm_tc_kernel(PlanView pv, const float* __restrict__ x /* tf32-rounded, 16B ali
         }
       }
       cp_async_commit_group();
+      if (trp) trace_put(trace, 1, k / kProducers, 6);
       __syncwarp();
       if (lane == 0) {
         mbar_arrive(meta_empty + 8 * ms);             // every lane has read the records
@@ -417,6 +444,7 @@ spmm_tc_kernel(PlanView pv, const float* __restrict__ x /* tf32-rounded, 16B ali
 #pragma unroll
       for (int j = 0; j < kG; ++j)
         if (j < nt) sts_v4(b_smem + s * C::kBStageBytes + j * kBTileBytes + lane * 16, bv[j]);
+      if (trp) trace_put(trace, 1, k / kProducers, 7);
     }
     // drain: publish the own stages still in flight
     cp_async_wait_all();
@@ -447,22 +475,54 @@ uint32_t kernel_flags() {
   return flags;
 }
 
-template <int DBLK, int OWN_LAG>
+// TCGNN_TRACE=<path>: after every launch, block 0's timeline is written to <path> (3 roles x 512 stages x 8 int64)
+long long* trace_buffer() {
+  static long long* buf = [] {
+    long long* p = nullptr;
+    if (getenv("TCGNN_TRACE") != nullptr) {
+      if (cudaMalloc(&p, sizeof(long long) * 3 * kTraceStages * 8) != cudaSuccess) p = nullptr;
+    }
+    return p;
+  }();
+  if (buf != nullptr) cudaMemset(buf, 0, sizeof(long long) * 3 * kTraceStages * 8);
+  return buf;
+}
+void trace_dump(const long long* trace, cudaStream_t stream) {
+  static long long host[3 * kTraceStages * 8];
+  if (cudaStreamSynchronize(stream) != cudaSuccess) return;
+  if (cudaMemcpy(host, trace, sizeof(host), cudaMemcpyDeviceToHost) != cudaSuccess) return;
+  if (FILE* f = fopen(getenv("TCGNN_TRACE"), "wb")) {
+    fwrite(host, 1, sizeof(host), f);
+    fclose(f);
+  }
+}
+
+template <class C, int DBLK>
 cudaError_t launch_kernel(const tcgnn_plan* plan, int grid, const float* xr, int64_t ldr, const float* wperm, float* y,
                           int64_t ldy, int32_t dim, cudaStream_t stream) {
-  using C = Cfg<DBLK>;
   static bool attr_set[64] = {};
   const int dev = plan->device;
   if (dev < 64 && !attr_set[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(spmm_tc_kernel<DBLK, OWN_LAG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(spmm_tc_kernel<C, DBLK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          C::kSmemBytes);
     if (e != cudaSuccess) return e;
     attr_set[dev] = true;
   }
-  spmm_tc_kernel<DBLK, OWN_LAG><<<grid, kThreads, C::kSmemBytes, stream>>>(plan->view(), xr, ldr, wperm, y, ldy, dim,
-                                                                            kernel_flags());
+  long long* trace = trace_buffer();
+  spmm_tc_kernel<C, DBLK><<<grid, C::kThreads, C::kSmemBytes, stream>>>(plan->view(), xr, ldr, wperm, y, ldy, dim,
+                                                                         kernel_flags(), trace);
   count_launch();
+  if (trace != nullptr) trace_dump(trace, stream);
   return cudaGetLastError();
+}
+
+// pipeline shape: env TCGNN_PRESET selects among the compiled variants (tuning; 0 = production)
+int preset_setting() {
+  static const int v = [] {
+    const char* e = getenv("TCGNN_PRESET");
+    return e ? atoi(e) : 0;
+  }();
+  return v;
 }
 
 template <int DBLK>
@@ -470,7 +530,19 @@ cudaError_t launch_pass(const tcgnn_plan* plan, int grid, const float* xr, int64
                         int64_t ldy, int32_t dim, cudaStream_t stream) {
   spmm_zero_partial_rows<<<grid, 128, 0, stream>>>(plan->view(), y, ldy, dim);
   count_launch();
-  return launch_kernel<DBLK, 1>(plan, grid, xr, ldr, wperm, y, ldy, dim, stream);
+  constexpr int T = 8 / DBLK;   // tiles in 32 KB of A
+#define TCGNN_LAUNCH(G, S, P, L) \
+  return launch_kernel<Cfg<DBLK, G, S, P, L>, DBLK>(plan, grid, xr, ldr, wperm, y, ldy, dim, stream)
+  switch (preset_setting()) {
+    case 1: TCGNN_LAUNCH(T, 6, 4, 2);
+    case 2: TCGNN_LAUNCH(T / 2, 12, 6, 2);
+    case 3: TCGNN_LAUNCH(T / 2, 12, 8, 1);
+    case 4: TCGNN_LAUNCH(T / 2, 12, 6, 1);
+    case 5: TCGNN_LAUNCH(T / 2, 12, 4, 2);
+    case 6: TCGNN_LAUNCH(T, 6, 8, 1);
+    default: TCGNN_LAUNCH(T, 6, 6, 1);
+  }
+#undef TCGNN_LAUNCH
 }
 
 }  // namespace
