@@ -360,14 +360,29 @@ def main():
     alg = algorithmic_bytes(args.op, local_rows, local_edges, dim)
     achieved = alg / (k_ms * 1e-3) / 1e9
     key = {"spmm": "spmm_tc_kernel", "sddmm": "sddmm_tc_kernel", "agnn": "spmm_tc_kernel"}[args.op]
+    traffic = ncu_traffic(f"{key}:{args.workload}:D{dim}") if world == 1 else None
     roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                "frac": round(achieved / peak, 4), "traffic": ncu_traffic(f"{key}:{args.workload}:D{dim}"),
+                "frac": round(achieved / peak, 4), "traffic": traffic,
                 "kernel": key, "kernel_ms": round(k_ms, 4), "algorithmic_bytes": alg,
                 "peak_source": peak_src,
                 "useful_gflops": round(2.0 * local_edges * dim * (2 if args.op == "agnn" else 1) / (k_ms * 1e-3) / 1e9, 1),
-                "note": "algorithmic bytes = no-reuse CSR gather model E(4D+4)+N(4D+4) (SURVEY.md 8d); X "
-                        + ("fits" if n * dim * 4 < 126e6 else "does not fit") + " in the 126 MB L2, so gathers are "
-                        "largely served by L2 and `traffic` (DRAM) is far below the algorithmic bytes"}
+                "note": "kernel_ms = the operator's launches (tf32 round/pack + clear of split windows + " + key + ", the "
+                        "last one ~98 % of it: profiles/*launches*.csv), CUDA events, L2 flushed; algorithmic bytes = "
+                        "no-reuse CSR gather model E(4D+4)+N(4D+4) (SURVEY.md 8d); X "
+                        + ("nearly fits" if n * dim * 4 < 126e6 else "does not fit") + " in the 126 MB L2 and condensed "
+                        "tiles fetch a column once per window, so DRAM `traffic` is below the algorithmic bytes and frac "
+                        "can exceed 1 -- the physical bound is then L2->SM gather bandwidth (see `l2_gather`)"}
+    if info is not None and args.op in ("spmm", "agnn", "sddmm"):
+        # bytes the kernel actually pulls through L2: 8 feature rows per 16x8 TC block (+ SDDMM: the window's own
+        # 16 rows per 16 blocks), against the ~6300 B/clk full-chip LTS cap of B300_MICROARCH.md at the SM clock
+        tiles = int(info[3])
+        per_tile = 8 * dim * 4 * (1 if args.op == "spmm" else (2.125 if args.op == "agnn" else 1.125))
+        sm_clk = (clocks or {}).get("sm_mhz") or 1965.0
+        cap = 6300.0 * sm_clk * 1e6 / 1e9
+        l2 = tiles * per_tile / (k_ms * 1e-3) / 1e9
+        roofline["l2_gather"] = {"bytes": int(tiles * per_tile), "achieved": round(l2, 1), "peak": round(cap, 1),
+                                 "unit": "GB/s", "frac": round(l2 / cap, 4),
+                                 "peak_source": "B300_MICROARCH.md LTS cap ~6300 B/clk x sampled SM clock"}
 
     # ---------------------------------------------------------------- end to end (host buffers)
     x_host = x_local.cpu().pin_memory()

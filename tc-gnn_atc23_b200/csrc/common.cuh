@@ -29,6 +29,7 @@ struct PlanView {  // device pointers, passed by value to kernels
   const TileMeta* tiles;        // [num_tiles]
   const int32_t* win_tile_ptr;  // [num_windows + 1] exclusive scan of blockPartition
   const int32_t* eperm;         // [num_pairs] tile order -> CSR edge id (lazy; weighted SpMM / SDDMM)
+  const int32_t* slice_ptr;     // [grid + 1] tile range of every persistent CTA (balanced by tiles + windows)
   int32_t num_nodes;            // rows of the plan
   int32_t num_cols;             // rows of X
   int32_t row_base;             // global id of row 0 (row panels)
@@ -187,6 +188,34 @@ __device__ __forceinline__ void tma_bulk_g2s_hint(uint32_t smem_dst, const void*
           smem_dst),
       "l"(gmem_src), "r"(bytes), "r"(bar), "l"(policy)
       : "memory");
+}
+
+// shared -> global bulk copies (TMA engine, SASS UBLKCP / UBLKRED): they do not queue behind the SM's
+// load/store pipeline.  Addresses 16-byte aligned, size a multiple of 16.  Tracked by bulk groups.
+__device__ __forceinline__ void tma_bulk_s2g(void* gmem_dst, uint32_t smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_src), "r"(bytes)
+               : "memory");
+}
+// global[i] += shared[i] (fp32), element-wise atomic at L2
+__device__ __forceinline__ void tma_bulk_s2g_add_f32(void* gmem_dst, uint32_t smem_src, uint32_t bytes) {
+  asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(gmem_dst),
+               "r"(smem_src), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void tma_bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_bulk_wait_group_read() {   // sources of all but the N newest groups have been read
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void tma_bulk_wait_group() {        // all but the N newest groups are complete
+  asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void named_barrier_sync(uint32_t id, uint32_t threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+__device__ __forceinline__ void sts_f32(uint32_t addr, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
 }
 
 // L2 eviction policies: feature rows are re-read by many windows (keep), the tile stream and the

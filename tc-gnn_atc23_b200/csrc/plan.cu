@@ -5,6 +5,7 @@
 // All work is on the device; the only host round trip is the tile total (needed to size the
 // allocation).  Integer-only, HBM-bound: plain coalesced kernels, grid-stride.
 #include <stdio.h>
+#include <stdlib.h>
 
 #include <new>
 
@@ -171,6 +172,25 @@ __global__ void scatter_edges_kernel(TileMeta* tiles, const int32_t* __restrict_
   }
 }
 
+// Tile range of every persistent CTA.  A CTA's time is ~ a * tiles + b * windows (every window costs an
+// accumulator hand-over and a 16 x D output tile; measured b / a = 4..14, profiles/r01e_*), so slices are
+// balanced on tiles + win_cost * windows, not on tiles alone: R-MAT graphs have long runs of 1-tile windows.
+__global__ void slice_bounds_kernel(const TileMeta* __restrict__ tiles, int32_t num_tiles, int32_t num_windows,
+                                    int32_t win_cost, int32_t grid, int32_t* __restrict__ slice_ptr) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > grid) return;
+  const int64_t total = static_cast<int64_t>(num_tiles) + static_cast<int64_t>(win_cost) * num_windows;
+  const int64_t target = total * i / grid;
+  // smallest t with cost(t) = t + win_cost * (windows begun before tile t) >= target
+  int32_t lo = 0, hi = num_tiles;
+  while (lo < hi) {
+    const int32_t mid = lo + (hi - lo) / 2;
+    const int64_t cost = mid + static_cast<int64_t>(win_cost) * tiles[mid].win;
+    if (cost >= target) hi = mid; else lo = mid + 1;
+  }
+  slice_ptr[i] = i == grid ? num_tiles : (i == 0 ? 0 : lo);
+}
+
 __global__ void store_edge_ofs_kernel(TileMeta* tiles, const int32_t* __restrict__ tile_ofs, int32_t num_tiles) {
   for (int64_t g = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; g < num_tiles;
        g += static_cast<int64_t>(gridDim.x) * blockDim.x)
@@ -300,6 +320,21 @@ int plan_create(const int32_t* row_ptr, const int32_t* col_idx, const int32_t* b
     scratch = nullptr;
     PLAN_CUDA(cudaFree(tile_ofs));
     tile_ofs = nullptr;
+    // one persistent CTA per SM (fewer for tiny graphs: >= 8 tiles per CTA)
+    p->grid = p->num_sms;
+    if (p->num_tiles < p->grid * 8) p->grid = p->num_tiles / 8;
+    if (p->grid < 1) p->grid = 1;
+    static const int win_cost = [] {
+      const char* e = getenv("TCGNN_WIN_COST");
+      const int v = e ? atoi(e) : 3;
+      return v < 0 ? 0 : (v > 64 ? 64 : v);
+    }();
+    PLAN_CUDA(cudaMalloc(&p->slice_ptr, sizeof(int32_t) * (static_cast<size_t>(p->grid) + 1)));
+    slice_bounds_kernel<<<(p->grid + 256) / 256, 256, 0, stream>>>(p->tiles, p->num_tiles, num_windows, win_cost,
+                                                                   p->grid, p->slice_ptr);
+    count_launch();
+    PLAN_CUDA(cudaGetLastError());
+    PLAN_CUDA(cudaStreamSynchronize(stream));
   }
   *plan_out = p;
   return TCGNN_OK;
@@ -393,6 +428,7 @@ int plan_destroy(tcgnn_plan* p) {
   if (p == nullptr) return TCGNN_OK;
   if (p->tiles) cudaFree(p->tiles);
   if (p->win_tile_ptr) cudaFree(p->win_tile_ptr);
+  if (p->slice_ptr) cudaFree(p->slice_ptr);
   if (p->eperm) cudaFree(p->eperm);
   if (p->weight_perm) cudaFree(p->weight_perm);
   if (p->sddmm_perm) cudaFree(p->sddmm_perm);

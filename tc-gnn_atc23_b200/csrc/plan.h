@@ -24,6 +24,8 @@ struct tcgnn_plan {
   // owned device memory
   tcgnn::TileMeta* tiles = nullptr;   // [num_tiles + 1]
   int32_t* win_tile_ptr = nullptr;    // [num_windows + 1]
+  int32_t* slice_ptr = nullptr;       // [grid + 1] tile range per persistent CTA
+  int grid = 1;                       // persistent CTAs the kernels are launched with
   int32_t* eperm = nullptr;           // [num_pairs]   lazy (weighted SpMM / SDDMM)
   float* weight_perm = nullptr;       // [num_pairs]   lazy: edge weights in tile order
   float* sddmm_perm = nullptr;        // [num_pairs]   lazy: SDDMM results in tile order
@@ -39,6 +41,7 @@ struct tcgnn_plan {
     v.tiles = tiles;
     v.win_tile_ptr = win_tile_ptr;
     v.eperm = eperm;
+    v.slice_ptr = slice_ptr;
     v.num_nodes = num_nodes;
     v.num_cols = num_cols;
     v.row_base = row_base;

@@ -83,10 +83,9 @@ sddmm_tc_kernel(PlanView pv, const int4* __restrict__ groups, int32_t num_groups
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int64_t nt = pv.num_tiles;
-  const int32_t g_lo = first_group_at_or_after(groups, num_groups, static_cast<int32_t>(nt * blockIdx.x / gridDim.x));
-  const int32_t g_hi =
-      first_group_at_or_after(groups, num_groups, static_cast<int32_t>(nt * (blockIdx.x + 1) / gridDim.x));
+  // the plan's cost-balanced tile slices (launched with plan->grid CTAs), rounded to group boundaries
+  const int32_t g_lo = first_group_at_or_after(groups, num_groups, pv.slice_ptr[blockIdx.x]);
+  const int32_t g_hi = first_group_at_or_after(groups, num_groups, pv.slice_ptr[blockIdx.x + 1]);
   const int32_t n_groups = g_hi - g_lo;
   const int32_t nkc = (dim + 31) >> 5;          // 32-feature chunks
   const int32_t n_stages = n_groups * nkc;
@@ -308,9 +307,7 @@ int sddmm_launch(tcgnn_plan* plan, const float* x, int64_t ldx, float* edge_out,
     }
     attr_set[plan->device] = true;
   }
-  int grid = plan->num_sms;
-  if (plan->num_groups < grid * 2) grid = plan->num_groups / 2;
-  if (grid < 1) grid = 1;
+  const int grid = plan->grid;
   const int64_t ldr = (static_cast<int64_t>(dim) + 3) / 4 * 4;
   const float* xr = nullptr;
   st = round_pack_launch(plan, x, ldx, dim, ldr, stream, &xr);

@@ -57,6 +57,7 @@ constexpr int kBTileBytes = TCGNN_BLK_H * TCGNN_BLK_W * 4;  // 512
 // ablation switches (env TCGNN_ABLATE, profiling only -- results are wrong when set): skip the row
 // gathers / the MMAs after a window's first / the B-tile construction / all but one MMA of a full stage
 constexpr uint32_t kAblateGather = 1u, kAblateMma = 2u, kAblateBuild = 4u, kAblateMmaFast = 8u;
+constexpr uint32_t kAblateOutput = 256u;   // no bulk output stores
 // L2 policy switches (env TCGNN_TUNE overrides the default kTuneDefault): feature-row gathers evict_last /
 // tile stream evict_first / output rows written with streaming stores
 constexpr uint32_t kTuneXLast = 16u, kTuneMetaFirst = 32u, kTuneYStream = 64u;
@@ -64,8 +65,10 @@ constexpr uint32_t kTuneDefault = kTuneXLast | kTuneMetaFirst | kTuneYStream;
 
 // DBLK: 128-feature blocks per pass; G: tiles per pipeline stage; S: data stages; P: producer warps;
 // L: own stages a producer warp keeps in flight before it publishes the oldest
-template <int DBLK, int G, int S_, int P, int L>
+// STAGED: the epilogue stages a window's output in shared memory and writes it with one bulk copy
+template <int DBLK, int G, int S_, int P, int L, bool STAGED>
 struct Cfg {
+  static constexpr bool kStaged = STAGED;
   static constexpr int kG = G;
   static constexpr int kATileBytes = DBLK * 4096;              // DBLK*4 swizzle atoms of 8 rows x 128 B
   static constexpr int kAStageBytes = kG * kATileBytes;
@@ -78,8 +81,10 @@ struct Cfg {
   static constexpr int kMetaStages = 16;                       // tile-record ring, prefetched far ahead of the data
   static constexpr uint32_t kTmemCols = kAcc * DBLK * 16;      // 64 / 128
   static constexpr int kBarBytes = (2 * kMetaStages + 2 * kStages + 2 * kAcc) * 8;
-  static constexpr int kSmemBytes = kStages * (kAStageBytes + kBStageBytes) + kMetaStages * kMetaStageBytes +
-                                    kBarBytes + kStages * 4 /*info words*/ + 16 + 1024 /*alignment slack*/;
+  static constexpr int kYStageBytes = STAGED ? TCGNN_BLK_H * DBLK * 128 * 4 : 0;   // one window of output (8 / 16 KB)
+  static constexpr int kSmemBytes = kStages * (kAStageBytes + kBStageBytes) + 2 * kYStageBytes +
+                                    kMetaStages * kMetaStageBytes + kBarBytes + kStages * 4 /*info words*/ + 16 +
+                                    1024 /*alignment slack*/;
   static_assert(kG >= 1 && kG <= 8, "the open/close word holds 8 tile bits");
   static_assert(kSmemBytes <= 232448, "exceeds the 227 KB of dynamic shared memory per CTA");
   static_assert(kMetaStages >= (L + 1) * P || kMetaStages >= 16, "records of every in-flight own stage stay resident");
@@ -94,15 +99,10 @@ struct SliceInfo {
   bool partial_last;     // last window ends after t1      -> atomics
 };
 
-__device__ __forceinline__ void slice_range(int32_t num_tiles, int32_t& t0, int32_t& t1) {
-  const int64_t nt = num_tiles;
-  t0 = static_cast<int32_t>(nt * blockIdx.x / gridDim.x);
-  t1 = static_cast<int32_t>(nt * (blockIdx.x + 1) / gridDim.x);
-}
-
 __device__ __forceinline__ SliceInfo slice_info(const PlanView& pv) {
   SliceInfo s;
-  slice_range(pv.num_tiles, s.t0, s.t1);
+  s.t0 = pv.slice_ptr[blockIdx.x];   // the kernels are launched with plan->grid CTAs
+  s.t1 = pv.slice_ptr[blockIdx.x + 1];
   s.w_first = 0;
   s.n_windows = 0;
   s.partial_first = s.partial_last = false;
@@ -143,6 +143,8 @@ __global__ void permute_weights_kernel(const int32_t* __restrict__ eperm, const 
 // Timeline probe (env TCGNN_TRACE=1, tools/trace.py): block 0 records clock64 at fixed points of the first
 // kTraceStages stages -- role 0 = MMA warp, 1 = producer warp 0, 2 = meta loader; 8 points per stage.
 constexpr int kTraceStages = 512;
+constexpr int kTraceCtas = 160;             // + per-CTA {cycles, tiles, windows, 0}
+constexpr int kTraceWords = 3 * kTraceStages * 8 + kTraceCtas * 4 + kTraceStages * 8;   // + epilogue warp 0, per window
 __device__ __forceinline__ void trace_put(long long* trace, int role, int32_t k, int point) {
   if (k < kTraceStages && (threadIdx.x & 31) == 0) trace[(role * kTraceStages + k) * 8 + point] = clock64();
 }
@@ -163,7 +165,8 @@ spmm_tc_kernel(PlanView pv, const float* __restrict__ x /* tf32-rounded, 16B ali
   const uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_smem = smem;                                       // [S][G][DBLK*4 atoms][8][128B]
   const uint32_t b_smem = a_smem + S * C::kAStageBytes;               // [S][G][512B]
-  const uint32_t m_smem = b_smem + S * C::kBStageBytes;               // [MS][G] TileMeta
+  const uint32_t y_smem = b_smem + S * C::kBStageBytes;               // [2][16][dim] output staging (bulk stores)
+  const uint32_t m_smem = y_smem + 2 * C::kYStageBytes;               // [MS][G] TileMeta
   const uint32_t bars = m_smem + MS * C::kMetaStageBytes;
   const uint32_t meta_full = bars, meta_empty = bars + 8 * MS;
   const uint32_t full = bars + 16 * MS, empty = full + 8 * S;
@@ -176,7 +179,8 @@ spmm_tc_kernel(PlanView pv, const float* __restrict__ x /* tf32-rounded, 16B ali
   const SliceInfo sl = slice_info(pv);
   const int32_t n_tiles = sl.t1 - sl.t0;
   const int32_t n_stages = (n_tiles + kG - 1) / kG;
-  const bool tr = trace != nullptr && blockIdx.x == 0;
+  const bool tr = trace != nullptr && blockIdx.x == ((flags >> 16) & 0xFFu);   // env TCGNN_TRACE_CTA
+  const long long t_start = clock64();
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < MS; ++s) {
@@ -201,15 +205,28 @@ spmm_tc_kernel(PlanView pv, const float* __restrict__ x /* tf32-rounded, 16B ali
 
   if (warp < kEpiWarps) {
     // ===================================== epilogue =====================================
+    // TMEM -> registers -> row-major staging tile in shared memory -> one bulk copy per output row (TMA engine).
+    // Plain st.global from here queue behind the producers' gathers in the SM's load/store pipeline: ~120
+    // cycles per store instruction, 3800 cycles per window at D = 256 (profiles/r01e_*trace*).  Windows cut by
+    // a slice boundary use the bulk reduce-add instead of fp32 atomics.
     const int q = warp;  // TMEM lane quadrant == warp id % 4
     const bool stream_y = (flags & kTuneYStream) != 0;
+    // one bulk copy per window needs a contiguous, 16-byte aligned output panel
+    const bool bulk = C::kStaged && ldy == dim && (dim & 3) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0;
+    const bool issuer = threadIdx.x == 0;
+    const uint32_t row_bytes = static_cast<uint32_t>(dim) * 4u;
     for (int32_t wl = 0; wl < sl.n_windows; ++wl) {
       const int b = wl % kAcc;
+      const bool tre = tr && q == 0 && wl < kTraceStages;
+      long long* trow = trace + 3 * kTraceStages * 8 + kTraceCtas * 4 + wl * 8;
+      if (tre && lane == 0) trow[0] = clock64();
       mbar_wait_backoff(acc_full + 8 * b, (wl / kAcc) & 1);
       tc_fence_after();
+      if (tre && lane == 0) trow[1] = clock64();
       const int32_t w = sl.w_first + wl;
       const bool use_atomic = (wl == 0 && sl.partial_first) || (wl == sl.n_windows - 1 && sl.partial_last);
       const int32_t row0 = w * TCGNN_BLK_H;
+      const uint32_t ybuf = y_smem + (wl & 1) * C::kYStageBytes;
 #pragma unroll
       for (int m = 0; m < DBLK; ++m) {
         const int f = m * 128 + q * 32 + lane;       // feature owned by this thread
@@ -217,23 +234,46 @@ spmm_tc_kernel(PlanView pv, const float* __restrict__ x /* tf32-rounded, 16B ali
           uint32_t v[16];
           tmem_ld_32x32b_x16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (b * DBLK + m) * 16, v);
           tmem_ld_wait();
+          if (tre && lane == 0) trow[2 + m] = clock64();
           if (f < dim) {
-            float* yp = y + static_cast<int64_t>(row0) * ldy + f;
+            if (bulk) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              if (row0 + i < pv.num_nodes) {
-                if (use_atomic) atomicAdd(yp + i * ldy, __uint_as_float(v[i]));
-                else if (stream_y) __stcs(yp + i * ldy, __uint_as_float(v[i]));
-                else yp[i * ldy] = __uint_as_float(v[i]);
+              for (int i = 0; i < 16; ++i) sts_f32(ybuf + i * row_bytes + f * 4, __uint_as_float(v[i]));
+            } else {
+              float* yp = y + static_cast<int64_t>(row0) * ldy + f;
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                if (row0 + i < pv.num_nodes) {
+                  if (use_atomic) atomicAdd(yp + i * ldy, __uint_as_float(v[i]));
+                  else if (stream_y) __stcs(yp + i * ldy, __uint_as_float(v[i]));
+                  else yp[i * ldy] = __uint_as_float(v[i]);
+                }
               }
             }
           }
         }
       }
+      if (tre && lane == 0) trow[4] = clock64();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(acc_empty + 8 * b);
+      if (lane == 0) mbar_arrive(acc_empty + 8 * b);   // the accumulator is in registers / shared memory now
+      if (bulk) {
+        fence_proxy_async_smem();                      // staging writes -> visible to the bulk copies
+        // the copies of window wl-1 have read the other buffer: after the barrier everybody may overwrite it
+        if (issuer) tma_bulk_wait_group_read<0>();
+        named_barrier_sync(1, kEpiWarps * 32);
+        if (issuer && !(flags & kAblateOutput)) {
+          const int rows = min(TCGNN_BLK_H, pv.num_nodes - row0);
+          float* yp = y + static_cast<int64_t>(row0) * ldy;
+          // contiguous output: the window's rows are one block (a bulk copy costs ~200 cycles whatever its size)
+          if (use_atomic) tma_bulk_s2g_add_f32(yp, ybuf, rows * row_bytes);
+          else tma_bulk_s2g(yp, ybuf, rows * row_bytes);
+          tma_bulk_commit_group();
+        }
+      }
+      if (tre && lane == 0) trow[5] = clock64();
     }
+    if (bulk && issuer) tma_bulk_wait_group<0>();      // shared memory must outlive the copies
   } else if (warp == kMmaWarp) {
     // ===================================== MMA issuer ===================================
     // The whole warp runs the loop (warp-uniform control flow keeps addresses and descriptors in uniform
@@ -457,6 +497,13 @@ spmm_tc_kernel(PlanView pv, const float* __restrict__ x /* tf32-rounded, 16B ali
   // ===================================== teardown =======================================
   tc_fence_before();
   __syncthreads();
+  if (trace != nullptr && threadIdx.x == 0 && blockIdx.x < kTraceCtas) {
+    long long* row = trace + 3 * kTraceStages * 8 + blockIdx.x * 4;
+    row[0] = clock64() - t_start;
+    row[1] = n_tiles;
+    row[2] = sl.n_windows;
+    row[3] = 0;
+  }
   if (warp == kMmaWarp) {
     tc_fence_after();
     tmem_dealloc<C::kTmemCols>(tmem_base);
@@ -467,10 +514,12 @@ uint32_t kernel_flags() {
   static const uint32_t flags = [] {
     const char* a = getenv("TCGNN_ABLATE");
     const char* t = getenv("TCGNN_TUNE");
-    const uint32_t ablate = a ? static_cast<uint32_t>(strtoul(a, nullptr, 0)) & 15u : 0u;
+    const uint32_t ablate = a ? static_cast<uint32_t>(strtoul(a, nullptr, 0)) & 0x30Fu : 0u;
     const uint32_t tune = t ? static_cast<uint32_t>(strtoul(t, nullptr, 0)) & (kTuneXLast | kTuneMetaFirst | kTuneYStream)
                             : kTuneDefault;
-    return ablate | tune;
+    const char* c = getenv("TCGNN_TRACE_CTA");
+    const uint32_t cta = c ? (static_cast<uint32_t>(atoi(c)) & 0xFFu) << 16 : 0u;   // bits [16,24)
+    return ablate | tune | cta;
   }();
   return flags;
 }
@@ -480,15 +529,15 @@ long long* trace_buffer() {
   static long long* buf = [] {
     long long* p = nullptr;
     if (getenv("TCGNN_TRACE") != nullptr) {
-      if (cudaMalloc(&p, sizeof(long long) * 3 * kTraceStages * 8) != cudaSuccess) p = nullptr;
+      if (cudaMalloc(&p, sizeof(long long) * kTraceWords) != cudaSuccess) p = nullptr;
     }
     return p;
   }();
-  if (buf != nullptr) cudaMemset(buf, 0, sizeof(long long) * 3 * kTraceStages * 8);
+  if (buf != nullptr) cudaMemset(buf, 0, sizeof(long long) * kTraceWords);
   return buf;
 }
 void trace_dump(const long long* trace, cudaStream_t stream) {
-  static long long host[3 * kTraceStages * 8];
+  static long long host[kTraceWords];
   if (cudaStreamSynchronize(stream) != cudaSuccess) return;
   if (cudaMemcpy(host, trace, sizeof(host), cudaMemcpyDeviceToHost) != cudaSuccess) return;
   if (FILE* f = fopen(getenv("TCGNN_TRACE"), "wb")) {
@@ -531,16 +580,20 @@ cudaError_t launch_pass(const tcgnn_plan* plan, int grid, const float* xr, int64
   spmm_zero_partial_rows<<<grid, 128, 0, stream>>>(plan->view(), y, ldy, dim);
   count_launch();
   constexpr int T = 8 / DBLK;   // tiles in 32 KB of A
-#define TCGNN_LAUNCH(G, S, P, L) \
-  return launch_kernel<Cfg<DBLK, G, S, P, L>, DBLK>(plan, grid, xr, ldr, wperm, y, ldy, dim, stream)
-  switch (preset_setting()) {
-    case 1: TCGNN_LAUNCH(T, 6, 4, 2);
-    case 2: TCGNN_LAUNCH(T / 2, 12, 6, 2);
-    case 3: TCGNN_LAUNCH(T / 2, 12, 8, 1);
-    case 4: TCGNN_LAUNCH(T / 2, 12, 6, 1);
-    case 5: TCGNN_LAUNCH(T / 2, 12, 4, 2);
-    case 6: TCGNN_LAUNCH(T, 6, 8, 1);
-    default: TCGNN_LAUNCH(T, 6, 6, 1);
+#define TCGNN_LAUNCH(G, S, P, STAGED) \
+  return launch_kernel<Cfg<DBLK, G, S, P, 1, STAGED>, DBLK>(plan, grid, xr, ldr, wperm, y, ldy, dim, stream)
+  // Dense windows (hundreds of tiles each: reddit): the deepest ring, output written straight from registers
+  // (rare).  Sparse windows: one output tile every few tiles -- stage it and hand it to the TMA engine; the
+  // staging buffers cost one pipeline slot.
+  int preset = preset_setting();
+  if (preset == 0) preset = static_cast<int64_t>(plan->num_tiles) >= 256LL * plan->num_windows ? 1 : 2;
+  switch (preset) {
+    case 1: TCGNN_LAUNCH(T, 6, 6, false);
+    case 3: TCGNN_LAUNCH(T - 1, 6, 6, true);
+    case 4: TCGNN_LAUNCH(T - 1, 6, 5, true);
+    case 5: TCGNN_LAUNCH(T, 5, 4, true);
+    case 6: TCGNN_LAUNCH(T, 5, 5, false);
+    default: TCGNN_LAUNCH(T, 5, 5, true);
   }
 #undef TCGNN_LAUNCH
 }
@@ -568,10 +621,8 @@ int spmm_launch(tcgnn_plan* plan, const float* x, int64_t ldx, const float* edge
     int st = round_pack_launch(plan, x, ldx, dim, ldr, stream, &xr);
     if (st != TCGNN_OK) return st;
   }
-  // one CTA per SM, each owning an equal slice of the tile stream (>= 8 tiles per CTA)
-  int grid = plan->num_sms;
-  if (plan->num_tiles < grid * 8) grid = plan->num_tiles / 8;
-  if (grid < 1) grid = 1;
+  // one persistent CTA per SM, each owning a slice of the tile stream (plan->slice_ptr)
+  const int grid = plan->grid;
   for (int32_t f0 = 0; f0 < dim; f0 += 256) {
     const int32_t d = dim - f0 < 256 ? dim - f0 : 256;
     cudaError_t e = d > 128 ? launch_pass<2>(plan, grid, xr + f0, ldr, wperm, y + f0, ldy, d, stream)
