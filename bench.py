@@ -268,6 +268,7 @@ def main():
     import torch.distributed as dist
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # stdout carries exactly one JSON line
         dist.init_process_group("nccl", device_id=dev)
     import TCGNN  # raises if the extension was not built: no fallback
     from sharding import RowPanel
@@ -322,17 +323,19 @@ def main():
         def step():
             return kernels(x_local)
     else:
+        pre = dim % 4 == 0   # round the local panel before the exchange: nobody re-rounds the gathered matrix
+
         def kernels(x_all):
             if args.op == "spmm":
-                return panel.spmm(x_all)
-            ef = panel.sddmm(x_all)
+                return panel.spmm(x_all, x_is_tf32=pre)
+            ef = panel.sddmm(x_all, x_is_tf32=pre)
             if args.op == "sddmm":
                 return ef
             att = torch.mm(ef.unsqueeze(-1), attention_w).transpose(0, 1).contiguous()
-            return panel.spmm(x_all, att)
+            return panel.spmm(x_all, att, x_is_tf32=pre)
 
         def step():
-            return kernels(panel.all_gather(x_local))
+            return kernels(panel.all_gather(x_local, round_tf32=pre))
 
     t0 = time.perf_counter()
     out = step()          # builds the plan (once per graph)
@@ -353,7 +356,7 @@ def main():
     if world == 1:
         k_in = x_local
     else:
-        k_in = panel.all_gather(x_local)
+        k_in = panel.all_gather(x_local, round_tf32=pre)
     kms, _ = timed_steps(lambda: kernels(k_in), args.steps, 3, flush, 1)
     k_ms = float(np.mean(kms))
     peak, peak_src = measured_peaks()
@@ -391,7 +394,7 @@ def main():
 
     def e2e_step():
         xd = x_host.to(dev, non_blocking=True)
-        y = kernels(xd) if world == 1 else kernels(panel.all_gather(xd))
+        y = kernels(xd) if world == 1 else kernels(panel.all_gather(xd, round_tf32=pre))
         y_host.copy_(y, non_blocking=True)
 
     ems, _ = timed_steps(e2e_step, args.steps, 3, flush, world)

@@ -110,6 +110,20 @@ int tcgnn_spmm_f32(tcgnn_plan* plan, const float* x, int64_t ldx, const float* e
 int tcgnn_sddmm_f32(tcgnn_plan* plan, const float* x, int64_t ldx, float* edge_out, int32_t dim,
                     void* stream);
 
+/* Pre-rounded operands.  The kernels consume cvt.rna.tf32(X) (what the reference's wmma::__float_to_tf32 does per
+ * use, TCGNN_kernel.cu:436-444); tcgnn_spmm_f32 / tcgnn_sddmm_f32 make that copy on every call.  A caller that
+ * feeds the same X to several ops (AGNN: SDDMM + weighted SpMM) or that ships X between GPUs (row-panel
+ * sharding: round the local panel once, all-gather the rounded rows) rounds once with tcgnn_round_tf32 and passes
+ * TCGNN_X_IS_TF32 to the *_ex entry points.  The flag is honoured when x is 16-byte aligned and ldx % 4 == 0
+ * (otherwise the op packs a copy as usual).  out: [rows, ldo] with ldo % 4 == 0, 16-byte aligned; columns
+ * [dim, ldo) are zero-filled. */
+#define TCGNN_X_IS_TF32 1u
+int tcgnn_round_tf32(const float* x, int64_t ldx, float* out, int64_t ldo, int64_t rows, int32_t dim, void* stream);
+int tcgnn_spmm_f32_ex(tcgnn_plan* plan, const float* x, int64_t ldx, const float* edge_weight, float* y,
+                      int64_t ldy, int32_t dim, uint32_t flags, void* stream);
+int tcgnn_sddmm_f32_ex(tcgnn_plan* plan, const float* x, int64_t ldx, float* edge_out, int32_t dim,
+                       uint32_t flags, void* stream);
+
 /* Bring-up / layout diagnostics (used by tests/test_gpu_umma_layouts.py): copies the two byte images
  * into 1024-byte aligned shared memory, issues `ksteps` tcgen05.mma.kind::tf32 (M=128) whose
  * descriptors are adesc/bdesc (start-address field 0) plus the image base plus k*a_step_bytes /

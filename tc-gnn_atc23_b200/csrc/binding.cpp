@@ -167,7 +167,8 @@ void check_graph(const torch::Tensor& input, const torch::Tensor& nodePointer, c
 // ---------------------------------------------------------------------------------------------
 torch::Tensor run_spmm(const torch::Tensor& input, const torch::Tensor& nodePointer, const torch::Tensor& edgeList,
                        const torch::Tensor* edgeAttention, const torch::Tensor& blockPartition,
-                       const torch::Tensor& edgeToColumn, const torch::Tensor& edgeToRow, int64_t row_base) {
+                       const torch::Tensor& edgeToColumn, const torch::Tensor& edgeToRow, int64_t row_base,
+                       bool x_is_tf32 = false) {
   check_graph(input, nodePointer, edgeList, blockPartition, edgeToColumn, edgeToRow, row_base);
   const float* weights = nullptr;
   if (edgeAttention != nullptr) {
@@ -184,23 +185,24 @@ torch::Tensor run_spmm(const torch::Tensor& input, const torch::Tensor& nodePoin
                               row_base < 0 ? -1 : input.size(0), row_base < 0 ? 0 : row_base);
   auto output = torch::empty({nodePointer.size(0) - 1, input.size(1)}, input.options());
   auto stream = c10::cuda::getCurrentCUDAStream(input.get_device()).stream();
-  check_status(tcgnn_spmm_f32(plan, input.data_ptr<float>(), input.size(1), weights, output.data_ptr<float>(),
-                              output.size(1), static_cast<int32_t>(input.size(1)), stream),
+  check_status(tcgnn_spmm_f32_ex(plan, input.data_ptr<float>(), input.size(1), weights, output.data_ptr<float>(),
+                                 output.size(1), static_cast<int32_t>(input.size(1)),
+                                 x_is_tf32 ? TCGNN_X_IS_TF32 : 0u, stream),
                "tcgnn_spmm_f32");
   return output;
 }
 
 torch::Tensor run_sddmm(const torch::Tensor& input, const torch::Tensor& nodePointer, const torch::Tensor& edgeList,
                         const torch::Tensor& blockPartition, const torch::Tensor& edgeToColumn,
-                        const torch::Tensor& edgeToRow, int64_t row_base) {
+                        const torch::Tensor& edgeToRow, int64_t row_base, bool x_is_tf32 = false) {
   check_graph(input, nodePointer, edgeList, blockPartition, edgeToColumn, edgeToRow, row_base);
   c10::cuda::CUDAGuard guard(input.device());
   tcgnn_plan* plan = get_plan(nodePointer, edgeList, blockPartition, edgeToColumn, edgeToRow,
                               row_base < 0 ? -1 : input.size(0), row_base < 0 ? 0 : row_base);
   auto output = torch::empty({edgeList.size(0)}, input.options());
   auto stream = c10::cuda::getCurrentCUDAStream(input.get_device()).stream();
-  check_status(tcgnn_sddmm_f32(plan, input.data_ptr<float>(), input.size(1), output.data_ptr<float>(),
-                               static_cast<int32_t>(input.size(1)), stream),
+  check_status(tcgnn_sddmm_f32_ex(plan, input.data_ptr<float>(), input.size(1), output.data_ptr<float>(),
+                                  static_cast<int32_t>(input.size(1)), x_is_tf32 ? TCGNN_X_IS_TF32 : 0u, stream),
                "tcgnn_sddmm_f32");
   return output;
 }
@@ -228,24 +230,41 @@ std::vector<torch::Tensor> sddmm_forward(torch::Tensor input, torch::Tensor node
 // (tcgnn_plan_create_panel), `row_base` is the global id of the panel's first row.
 std::vector<torch::Tensor> panel_forward(torch::Tensor input, int64_t row_base, torch::Tensor nodePointer,
                                          torch::Tensor edgeList, torch::Tensor blockPartition,
-                                         torch::Tensor edgeToColumn, torch::Tensor edgeToRow) {
+                                         torch::Tensor edgeToColumn, torch::Tensor edgeToRow, bool x_is_tf32) {
   TORCH_CHECK(row_base >= 0, "row_base must be >= 0");
-  return {run_spmm(input, nodePointer, edgeList, nullptr, blockPartition, edgeToColumn, edgeToRow, row_base)};
+  return {run_spmm(input, nodePointer, edgeList, nullptr, blockPartition, edgeToColumn, edgeToRow, row_base, x_is_tf32)};
 }
 
 std::vector<torch::Tensor> panel_forward_AGNN(torch::Tensor input, int64_t row_base, torch::Tensor nodePointer,
                                               torch::Tensor edgeList, torch::Tensor edgeAttention,
                                               torch::Tensor blockPartition, torch::Tensor edgeToColumn,
-                                              torch::Tensor edgeToRow) {
+                                              torch::Tensor edgeToRow, bool x_is_tf32) {
   TORCH_CHECK(row_base >= 0, "row_base must be >= 0");
-  return {run_spmm(input, nodePointer, edgeList, &edgeAttention, blockPartition, edgeToColumn, edgeToRow, row_base)};
+  return {run_spmm(input, nodePointer, edgeList, &edgeAttention, blockPartition, edgeToColumn, edgeToRow, row_base,
+                   x_is_tf32)};
 }
 
 std::vector<torch::Tensor> panel_forward_ef(torch::Tensor input, int64_t row_base, torch::Tensor nodePointer,
                                             torch::Tensor edgeList, torch::Tensor blockPartition,
-                                            torch::Tensor edgeToColumn, torch::Tensor edgeToRow) {
+                                            torch::Tensor edgeToColumn, torch::Tensor edgeToRow, bool x_is_tf32) {
   TORCH_CHECK(row_base >= 0, "row_base must be >= 0");
-  return {run_sddmm(input, nodePointer, edgeList, blockPartition, edgeToColumn, edgeToRow, row_base)};
+  return {run_sddmm(input, nodePointer, edgeList, blockPartition, edgeToColumn, edgeToRow, row_base, x_is_tf32)};
+}
+
+// cvt.rna.tf32 of a feature matrix, once, for callers that feed several ops or ship X between GPUs
+// (pass the result with x_is_tf32 = true).  Rows are padded to a multiple of 4 floats only if needed.
+torch::Tensor round_tf32(torch::Tensor input) {
+  CHECK_INPUT(input);
+  CHECK_F32(input);
+  TORCH_CHECK(input.dim() == 2 && input.size(1) >= 1, "input must be [rows, dim]");
+  TORCH_CHECK(input.size(1) % 4 == 0, "round_tf32 needs dim % 4 == 0 (16-byte rows); pass the raw matrix to the ops instead");
+  c10::cuda::CUDAGuard guard(input.device());
+  auto out = torch::empty_like(input);
+  auto stream = c10::cuda::getCurrentCUDAStream(input.get_device()).stream();
+  check_status(tcgnn_round_tf32(input.data_ptr<float>(), input.size(1), out.data_ptr<float>(), out.size(1),
+                                input.size(0), static_cast<int32_t>(input.size(1)), stream),
+               "tcgnn_round_tf32");
+  return out;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -362,10 +381,18 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   // additions
   m.def("preprocess_panel", &preprocess_panel,
         "SGT of a row panel: (edgeList, nodePointer, num_rows, num_cols, blk_h, blk_w, bp, e2c, e2r)");
-  m.def("panel_forward", &panel_forward, "SpMM of a row panel: (X_all, row_base, nodePointer, edgeList, bp, e2c, e2r)");
+  namespace py = pybind11;
+  m.def("panel_forward", &panel_forward, "SpMM of a row panel: (X_all, row_base, nodePointer, edgeList, bp, e2c, e2r)",
+        py::arg("input"), py::arg("row_base"), py::arg("nodePointer"), py::arg("edgeList"), py::arg("blockPartition"),
+        py::arg("edgeToColumn"), py::arg("edgeToRow"), py::arg("x_is_tf32") = false);
   m.def("panel_forward_AGNN", &panel_forward_AGNN,
-        "weighted SpMM of a row panel: (X_all, row_base, nodePointer, edgeList, edgeAttention, bp, e2c, e2r)");
-  m.def("panel_forward_ef", &panel_forward_ef, "SDDMM of a row panel: (X_all, row_base, nodePointer, edgeList, bp, e2c, e2r)");
+        "weighted SpMM of a row panel: (X_all, row_base, nodePointer, edgeList, edgeAttention, bp, e2c, e2r)",
+        py::arg("input"), py::arg("row_base"), py::arg("nodePointer"), py::arg("edgeList"), py::arg("edgeAttention"),
+        py::arg("blockPartition"), py::arg("edgeToColumn"), py::arg("edgeToRow"), py::arg("x_is_tf32") = false);
+  m.def("panel_forward_ef", &panel_forward_ef, "SDDMM of a row panel: (X_all, row_base, nodePointer, edgeList, bp, e2c, e2r)",
+        py::arg("input"), py::arg("row_base"), py::arg("nodePointer"), py::arg("edgeList"), py::arg("blockPartition"),
+        py::arg("edgeToColumn"), py::arg("edgeToRow"), py::arg("x_is_tf32") = false);
+  m.def("round_tf32", &round_tf32, "cvt.rna.tf32 of a [rows, dim] CUDA matrix (dim % 4 == 0), for x_is_tf32 = True");
   m.def("clear_plan_cache", &clear_plan_cache, "Destroy all cached kernel plans");
   m.def("plan_info", &plan_info, "[num_nodes, num_edges, num_windows, num_tiles, plan_bytes, pairs, device, sms]");
   m.def("launch_count", [](bool reset) { return tcgnn_launch_count(reset ? 1 : 0); }, pybind11::arg("reset") = false,

@@ -140,22 +140,41 @@ static int check_op(const char* what, const tcgnn_plan* plan, const float* x, in
   return TCGNN_OK;
 }
 
-int tcgnn_spmm_f32(tcgnn_plan* plan, const float* x, int64_t ldx, const float* edge_weight, float* y, int64_t ldy,
-                   int32_t dim, void* stream) {
+int tcgnn_spmm_f32_ex(tcgnn_plan* plan, const float* x, int64_t ldx, const float* edge_weight, float* y, int64_t ldy,
+                      int32_t dim, uint32_t flags, void* stream) {
   int st = check_op("tcgnn_spmm_f32", plan, x, ldx, y, dim);
   if (st != TCGNN_OK) return st;
   if (ldy < dim) {
     set_last_error("tcgnn_spmm_f32: ldy < dim");
     return TCGNN_ERR_INVALID_ARG;
   }
-  return spmm_launch(plan, x, ldx, edge_weight, y, ldy, dim, static_cast<cudaStream_t>(stream));
+  return spmm_launch(plan, x, ldx, edge_weight, y, ldy, dim, flags, static_cast<cudaStream_t>(stream));
 }
 
-int tcgnn_sddmm_f32(tcgnn_plan* plan, const float* x, int64_t ldx, float* edge_out, int32_t dim, void* stream) {
+int tcgnn_spmm_f32(tcgnn_plan* plan, const float* x, int64_t ldx, const float* edge_weight, float* y, int64_t ldy,
+                   int32_t dim, void* stream) {
+  return tcgnn_spmm_f32_ex(plan, x, ldx, edge_weight, y, ldy, dim, 0u, stream);
+}
+
+int tcgnn_sddmm_f32_ex(tcgnn_plan* plan, const float* x, int64_t ldx, float* edge_out, int32_t dim, uint32_t flags,
+                       void* stream) {
   if (plan != nullptr && plan->num_edges == 0) return TCGNN_OK;
   int st = check_op("tcgnn_sddmm_f32", plan, x, ldx, edge_out, dim);
   if (st != TCGNN_OK) return st;
-  return sddmm_launch(plan, x, ldx, edge_out, dim, static_cast<cudaStream_t>(stream));
+  return sddmm_launch(plan, x, ldx, edge_out, dim, flags, static_cast<cudaStream_t>(stream));
+}
+
+int tcgnn_sddmm_f32(tcgnn_plan* plan, const float* x, int64_t ldx, float* edge_out, int32_t dim, void* stream) {
+  return tcgnn_sddmm_f32_ex(plan, x, ldx, edge_out, dim, 0u, stream);
+}
+
+int tcgnn_round_tf32(const float* x, int64_t ldx, float* out, int64_t ldo, int64_t rows, int32_t dim, void* stream) {
+  if (x == nullptr || out == nullptr || rows < 0 || dim < 1 || ldx < dim || ldo < dim || (ldo & 3) != 0 ||
+      (reinterpret_cast<uintptr_t>(out) & 15) != 0) {
+    set_last_error("tcgnn_round_tf32: bad argument (out must be 16-byte aligned with ldo %% 4 == 0)");
+    return TCGNN_ERR_INVALID_ARG;
+  }
+  return round_tf32_launch(x, ldx, out, ldo, rows, dim, static_cast<cudaStream_t>(stream));
 }
 
 int tcgnn_debug_umma(const void* a_image, int32_t a_bytes, const void* b_image, int32_t b_bytes, uint64_t adesc,

@@ -81,4 +81,22 @@ int round_pack_launch(tcgnn_plan* plan, const float* x, int64_t ldx, int32_t dim
   return TCGNN_OK;
 }
 
+int round_tf32_launch(const float* x, int64_t ldx, float* out, int64_t ldo, int64_t rows, int32_t dim,
+                      cudaStream_t stream) {
+  if (rows <= 0) return TCGNN_OK;
+  const int vec_ok = (reinterpret_cast<uintptr_t>(x) % 16 == 0) && (ldx % 4 == 0);
+  const int64_t total = rows * (ldo >> 2);
+  int64_t g = (total + 255) / 256;
+  if (g > 148 * 16) g = 148 * 16;
+  if (g < 1) g = 1;
+  tf32_round_pack_kernel<<<static_cast<int>(g), 256, 0, stream>>>(x, ldx, dim, rows, out, ldo, vec_ok);
+  count_launch();
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_last_error("tf32_round_pack_kernel launch failed: %s", cudaGetErrorString(e));
+    return TCGNN_ERR_CUDA;
+  }
+  return TCGNN_OK;
+}
+
 }  // namespace tcgnn

@@ -47,8 +47,9 @@ constexpr int kBStageBytes = TCGNN_BLK_H * 128;            // 16 rows x 32 float
 constexpr int kMetaTileBytes = kGroupTiles * static_cast<int>(sizeof(TileMeta));
 constexpr int kMetaStageBytes = kMetaTileBytes + 16;       // + header {tile_start, ntiles, win, 0}
 constexpr uint32_t kTmemCols = kAcc * 16;
-constexpr int kSmemBytes = kStages * (kAStageBytes + kBStageBytes) + kMetaStages * kMetaStageBytes +
-                           (2 * kMetaStages + 2 * kStages + 2 * kAcc) * 8 + 16 + 1024;
+constexpr int kOutStageBytes = kGroupTiles * TCGNN_BLK_H * TCGNN_BLK_W * 4;   // a group's edge values, compacted (8 KB)
+constexpr int kSmemBytes = kStages * (kAStageBytes + kBStageBytes) + 2 * kOutStageBytes +
+                           kMetaStages * kMetaStageBytes + (2 * kMetaStages + 2 * kStages + 2 * kAcc) * 8 + 16 + 1024;
 static_assert(kProducers <= kStages, "a warp may not wait for the slot of an own stage it has not published yet");
 static_assert(kMetaStages >= 2 * kProducers, "one feature chunk per group: every in-flight stage is another group");
 static_assert(kSmemBytes <= 232448, "exceeds the 227 KB of dynamic shared memory per CTA");
@@ -73,7 +74,8 @@ sddmm_tc_kernel(PlanView pv, const int4* __restrict__ groups, int32_t num_groups
   const uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_smem = smem;
   const uint32_t b_smem = a_smem + kStages * kAStageBytes;
-  const uint32_t m_smem = b_smem + kStages * kBStageBytes;
+  const uint32_t o_smem = b_smem + kStages * kBStageBytes;      // [2] compacted edge values of a group
+  const uint32_t m_smem = o_smem + 2 * kOutStageBytes;
   const uint32_t bars = m_smem + kMetaStages * kMetaStageBytes;
   const uint32_t meta_full = bars, meta_empty = bars + 8 * kMetaStages;
   const uint32_t full = bars + 16 * kMetaStages, empty = full + 8 * kStages;
@@ -113,9 +115,14 @@ sddmm_tc_kernel(PlanView pv, const int4* __restrict__ groups, int32_t num_groups
 
   if (warp < kEpiWarps) {
     // ===================================== epilogue =====================================
+    // The edge values of a group are one contiguous run of the tile-ordered output (tiles are consecutive, a
+    // tile's edges are in mask-bit order).  They are compacted in shared memory and written with coalesced
+    // stores: ~n/128 store instructions per thread instead of up to 16 scattered ones (a global store
+    // instruction costs ~100 cycles of the SM's load/store pipeline next to the gathers, spmm_tc.cu).
     const int q = warp;
     const int m = q * 32 + lane;       // condensed column inside the group
     const int tt = m >> 3, c = m & 7;  // tile inside the group, column inside the tile
+    const int tid = threadIdx.x;       // 0..127
     for (int32_t gl = 0; gl < n_groups; ++gl) {
       const int4 grp = groups[g_lo + gl];
       uint4 mask = make_uint4(0, 0, 0, 0);
@@ -125,6 +132,11 @@ sddmm_tc_kernel(PlanView pv, const int4* __restrict__ groups, int32_t num_groups
         mask = *reinterpret_cast<const uint4*>(t->mask);
         edge_ofs = t->edge_ofs;
       }
+      // first / one-past-last output index of the group (same addresses for all threads: broadcast loads)
+      const int32_t e0 = pv.tiles[grp.x].edge_ofs;
+      const TileMeta* tl = pv.tiles + grp.x + grp.y - 1;
+      const uint4 ml = *reinterpret_cast<const uint4*>(tl->mask);
+      const int32_t n_out = tl->edge_ofs + __popc(ml.x) + __popc(ml.y) + __popc(ml.z) + __popc(ml.w) - e0;
       const int b = gl % kAcc;
       mbar_wait_backoff(acc_full + 8 * b, (gl / kAcc) & 1);
       tc_fence_after();
@@ -135,8 +147,9 @@ sddmm_tc_kernel(PlanView pv, const int4* __restrict__ groups, int32_t num_groups
       __syncwarp();
       if (lane == 0) mbar_arrive(acc_empty + 8 * b);
       // bit (r*8+c): word r/4, bit (r%4)*8+c ; rank in bit order = position in tile-ordered output
+      const uint32_t obuf = o_smem + (gl & 1) * kOutStageBytes;
       const uint32_t mw[4] = {mask.x, mask.y, mask.z, mask.w};
-      int base_rank = 0;
+      int base_rank = edge_ofs - e0;
 #pragma unroll
       for (int wd = 0; wd < 4; ++wd) {
 #pragma unroll
@@ -144,11 +157,15 @@ sddmm_tc_kernel(PlanView pv, const int4* __restrict__ groups, int32_t num_groups
           const int bit = rr * 8 + c;
           if (mw[wd] & (1u << bit)) {
             const int rank = base_rank + __popc(mw[wd] & ((1u << bit) - 1u));
-            out_perm[edge_ofs + rank] = __uint_as_float(v[wd * 4 + rr]);
+            sts_u32(obuf + rank * 4, v[wd * 4 + rr]);
           }
         }
         base_rank += __popc(mw[wd]);
       }
+      // double-buffered: the barrier of group gl also orders everybody's reads of group gl-1's buffer before
+      // the writes of group gl+1 into it
+      named_barrier_sync(1, kEpiWarps * 32);
+      for (int i = tid; i < n_out; i += kEpiWarps * 32) out_perm[e0 + i] = __uint_as_float(lds_u32(obuf + i * 4));
     }
   } else if (warp == kMmaWarp) {
     // ===================================== MMA issuer ===================================
@@ -289,7 +306,8 @@ __global__ void unpermute_kernel(const int32_t* __restrict__ eperm, const float*
 
 }  // namespace
 
-int sddmm_launch(tcgnn_plan* plan, const float* x, int64_t ldx, float* edge_out, int32_t dim, cudaStream_t stream) {
+int sddmm_launch(tcgnn_plan* plan, const float* x, int64_t ldx, float* edge_out, int32_t dim, uint32_t op_flags,
+                 cudaStream_t stream) {
   if (plan->num_edges == 0) return TCGNN_OK;
   int st = plan_ensure_eperm(plan, stream);
   if (st != TCGNN_OK) return st;
@@ -308,10 +326,15 @@ int sddmm_launch(tcgnn_plan* plan, const float* x, int64_t ldx, float* edge_out,
     attr_set[plan->device] = true;
   }
   const int grid = plan->grid;
-  const int64_t ldr = (static_cast<int64_t>(dim) + 3) / 4 * 4;
+  int64_t ldr = (static_cast<int64_t>(dim) + 3) / 4 * 4;
   const float* xr = nullptr;
-  st = round_pack_launch(plan, x, ldx, dim, ldr, stream, &xr);
-  if (st != TCGNN_OK) return st;
+  if ((op_flags & TCGNN_X_IS_TF32) && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (ldx & 3) == 0) {
+    xr = x;
+    ldr = ldx;
+  } else {
+    st = round_pack_launch(plan, x, ldx, dim, ldr, stream, &xr);
+    if (st != TCGNN_OK) return st;
+  }
   if (static_cast<int64_t>(plan->num_pairs) < plan->num_edges) {
     // duplicated (row, col) pairs: only one edge of each pair receives the value (as in the reference)
     e = cudaMemsetAsync(edge_out, 0, sizeof(float) * static_cast<size_t>(plan->num_edges), stream);

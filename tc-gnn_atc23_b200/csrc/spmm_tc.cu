@@ -386,28 +386,59 @@ spmm_tc_kernel(PlanView pv, const float* __restrict__ x /* tf32-rounded, 16B ali
       mbar_wait(meta_full + 8 * ms, (k / MS) & 1);
       if (trp) trace_put(trace, 1, k / kProducers, 1);
       const uint32_t meta = m_smem + ms * C::kMetaStageBytes;
-      // B values of the stage (weighted: global loads, issued first so they overlap everything below)
+      // B values of the stage
       float4 bv[kG];
+      if (wperm == nullptr) {
+        // pattern: my four cells are four bits of one mask word
 #pragma unroll
-      for (int j = 0; j < kG; ++j) {
-        bv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (j < nt && !skip_build) {
-          const uint32_t mw = lds_u32(meta + j * 64 + 32 + bword * 4);
+        for (int j = 0; j < kG; ++j) {
+          const uint32_t mw = (j < nt && !skip_build) ? lds_u32(meta + j * 64 + 32 + bword * 4) : 0u;
           const uint32_t nib = (mw >> bshift) & 0xFu;
-          if (wperm == nullptr) {
-            bv[j].x = (nib & 1u) ? 1.0f : 0.0f;
-            bv[j].y = (nib & 2u) ? 1.0f : 0.0f;
-            bv[j].z = (nib & 4u) ? 1.0f : 0.0f;
-            bv[j].w = (nib & 8u) ? 1.0f : 0.0f;
-          } else if (nib != 0u) {
+          bv[j] = make_float4((nib & 1u) ? 1.0f : 0.0f, (nib & 2u) ? 1.0f : 0.0f, (nib & 4u) ? 1.0f : 0.0f,
+                              (nib & 8u) ? 1.0f : 0.0f);
+        }
+      } else {
+        // weighted: a tile's weights are one contiguous run of the tile-ordered array (mask-bit order).  One
+        // coalesced load per tile (all issued before any is used), then every lane picks its <= 4 values by
+        // rank with shuffles -- global load instructions are expensive next to the gathers.
+        uint32_t nibs[kG];
+        int ranks[kG];
+        int counts[kG];
+        float wv[kG];
+        const float* runs[kG];
+#pragma unroll
+        for (int j = 0; j < kG; ++j) {
+          nibs[j] = 0u;
+          ranks[j] = 0;
+          counts[j] = 0;
+          wv[j] = 0.0f;
+          runs[j] = wperm;
+          if (j < nt && !skip_build) {
+            const int4 m4 = lds_v4(meta + j * 64 + 32);
+            const uint32_t w0 = static_cast<uint32_t>(m4.x), w1 = static_cast<uint32_t>(m4.y),
+                           w2 = static_cast<uint32_t>(m4.z), w3 = static_cast<uint32_t>(m4.w);
+            const uint32_t mine = bword == 0 ? w0 : (bword == 1 ? w1 : (bword == 2 ? w2 : w3));
+            nibs[j] = (mine >> bshift) & 0xFu;
             // rank of the first of my four bits among the tile's set bits (bit order r*8+c)
-            int rank = __popc(mw & ((1u << bshift) - 1u));
-            for (int i = 0; i < bword; ++i) rank += __popc(lds_u32(meta + j * 64 + 32 + i * 4));
-            const float* wp = wperm + static_cast<int32_t>(lds_u32(meta + j * 64 + 52)) + rank;
-            if (nib & 1u) bv[j].x = __ldg(wp++);
-            if (nib & 2u) bv[j].y = __ldg(wp++);
-            if (nib & 4u) bv[j].z = __ldg(wp++);
-            if (nib & 8u) bv[j].w = __ldg(wp++);
+            ranks[j] = __popc(mine & ((1u << bshift) - 1u)) + (bword > 0 ? __popc(w0) : 0) +
+                       (bword > 1 ? __popc(w1) : 0) + (bword > 2 ? __popc(w2) : 0);
+            counts[j] = __popc(w0) + __popc(w1) + __popc(w2) + __popc(w3);
+            runs[j] = wperm + static_cast<int32_t>(lds_u32(meta + j * 64 + 52));
+            if (counts[j] <= 32 && lane < counts[j]) wv[j] = __ldg(runs[j] + lane);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < kG; ++j) {
+          const uint32_t nib = nibs[j];
+          const int r0 = ranks[j], r1 = r0 + (nib & 1u), r2 = r1 + ((nib >> 1) & 1u), r3 = r2 + ((nib >> 2) & 1u);
+          if (counts[j] <= 32) {   // warp-uniform
+            const float x0 = __shfl_sync(0xffffffffu, wv[j], r0 & 31), x1 = __shfl_sync(0xffffffffu, wv[j], r1 & 31),
+                        x2 = __shfl_sync(0xffffffffu, wv[j], r2 & 31), x3 = __shfl_sync(0xffffffffu, wv[j], r3 & 31);
+            bv[j] = make_float4((nib & 1u) ? x0 : 0.0f, (nib & 2u) ? x1 : 0.0f, (nib & 4u) ? x2 : 0.0f,
+                                (nib & 8u) ? x3 : 0.0f);
+          } else {                 // dense tile (> 32 of 128 cells): direct loads
+            bv[j] = make_float4((nib & 1u) ? __ldg(runs[j] + r0) : 0.0f, (nib & 2u) ? __ldg(runs[j] + r1) : 0.0f,
+                                (nib & 4u) ? __ldg(runs[j] + r2) : 0.0f, (nib & 8u) ? __ldg(runs[j] + r3) : 0.0f);
           }
         }
       }
@@ -601,7 +632,7 @@ cudaError_t launch_pass(const tcgnn_plan* plan, int grid, const float* xr, int64
 }  // namespace
 
 int spmm_launch(tcgnn_plan* plan, const float* x, int64_t ldx, const float* edge_weight, float* y, int64_t ldy,
-                int32_t dim, cudaStream_t stream) {
+                int32_t dim, uint32_t op_flags, cudaStream_t stream) {
   const float* wperm = nullptr;
   if (edge_weight != nullptr && plan->num_pairs > 0) {
     int st = plan_ensure_eperm(plan, stream);
@@ -615,9 +646,12 @@ int spmm_launch(tcgnn_plan* plan, const float* x, int64_t ldx, const float* edge
     wperm = plan->weight_perm;
   }
   // Xr = tf32_rna(X), packed [num_cols, ldr] with ldr % 4 == 0 (16-byte aligned rows)
-  const int64_t ldr = (static_cast<int64_t>(dim) + 3) / 4 * 4;
+  int64_t ldr = (static_cast<int64_t>(dim) + 3) / 4 * 4;
   const float* xr = nullptr;
-  {
+  if ((op_flags & TCGNN_X_IS_TF32) && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (ldx & 3) == 0) {
+    xr = x;      // the caller rounded X already (tcgnn_round_tf32) and its rows are 16-byte aligned
+    ldr = ldx;
+  } else {
     int st = round_pack_launch(plan, x, ldx, dim, ldr, stream, &xr);
     if (st != TCGNN_OK) return st;
   }

@@ -97,12 +97,18 @@ class RowPanel:
     def panel_rows(self, g: int) -> int:
         return self.bounds[g + 1] - self.bounds[g]
 
-    def all_gather(self, x_local: torch.Tensor, group=None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    def all_gather(self, x_local: torch.Tensor, group=None, out: Optional[torch.Tensor] = None,
+                   round_tf32: bool = False) -> torch.Tensor:
         """The per-layer exchange: every rank contributes its [num_rows, D] panel, all receive the
-        [num_cols, D] matrix (one all-gather; uneven panels)."""
+        [num_cols, D] matrix (one all-gather; uneven panels).  With `round_tf32` (CUDA, D % 4 == 0) the
+        panel is rounded to TF32 before it is sent, so no rank has to round the whole gathered matrix
+        again: pass the result to spmm / sddmm with x_is_tf32=True."""
         if x_local.shape[0] != self.num_rows:
             raise ValueError(f"x_local has {x_local.shape[0]} rows, the panel has {self.num_rows}")
         d = x_local.shape[1]
+        if round_tf32 and self.num_rows > 0:
+            import TCGNN
+            x_local = TCGNN.round_tf32(x_local.contiguous())
         if out is None:
             if self._x_all is None or self._x_all.shape[1] != d or self._x_all.device != x_local.device \
                     or self._x_all.dtype != x_local.dtype:
@@ -124,29 +130,36 @@ class RowPanel:
         return out
 
     # ------------------------------------------------------------------ compute (GPU only)
-    def spmm(self, x_all: torch.Tensor, edge_attention: Optional[torch.Tensor] = None) -> torch.Tensor:
+    def spmm(self, x_all: torch.Tensor, edge_attention: Optional[torch.Tensor] = None,
+             x_is_tf32: bool = False) -> torch.Tensor:
         import TCGNN
         if self.num_rows == 0:
             return x_all.new_zeros((0, x_all.shape[1]))
         if edge_attention is None:
-            return TCGNN.panel_forward(x_all, self.row_base, *self.graph)[0]
+            return TCGNN.panel_forward(x_all, self.row_base, *self.graph, x_is_tf32=x_is_tf32)[0]
         rp, ci, bp, e2c, e2r = self.graph
-        return TCGNN.panel_forward_AGNN(x_all, self.row_base, rp, ci, edge_attention, bp, e2c, e2r)[0]
+        return TCGNN.panel_forward_AGNN(x_all, self.row_base, rp, ci, edge_attention, bp, e2c, e2r,
+                                        x_is_tf32=x_is_tf32)[0]
 
-    def sddmm(self, x_all: torch.Tensor) -> torch.Tensor:
+    def sddmm(self, x_all: torch.Tensor, x_is_tf32: bool = False) -> torch.Tensor:
         import TCGNN
         if self.num_rows == 0:
             return x_all.new_zeros((0,))
-        return TCGNN.panel_forward_ef(x_all, self.row_base, *self.graph)[0]
+        return TCGNN.panel_forward_ef(x_all, self.row_base, *self.graph, x_is_tf32=x_is_tf32)[0]
+
+    def _can_preround(self, x_local: torch.Tensor) -> bool:
+        return x_local.is_cuda and x_local.shape[1] % 4 == 0
 
     def aggregate(self, x_local: torch.Tensor, group=None) -> torch.Tensor:
         """GCN/GIN/SAG aggregation of one layer: all-gather + panel SpMM -> the panel of A.X."""
-        return self.spmm(self.all_gather(x_local, group))
+        pre = self._can_preround(x_local)
+        return self.spmm(self.all_gather(x_local, group, round_tf32=pre), x_is_tf32=pre)
 
     def agnn_aggregate(self, x_local: torch.Tensor, attention_w: torch.Tensor, group=None):
         """AGNN aggregation (reference gnn_conv.py:125-132) on the panel: one gather serves SDDMM and
         the weighted SpMM.  Returns (Y_panel, edge_feature_panel)."""
-        x_all = self.all_gather(x_local, group)
-        ef = self.sddmm(x_all)
+        pre = self._can_preround(x_local)
+        x_all = self.all_gather(x_local, group, round_tf32=pre)
+        ef = self.sddmm(x_all, x_is_tf32=pre)
         att = torch.mm(ef.unsqueeze(-1), attention_w).transpose(0, 1).contiguous()
-        return self.spmm(x_all, att), ef
+        return self.spmm(x_all, att, x_is_tf32=pre), ef

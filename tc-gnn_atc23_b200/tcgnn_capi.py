@@ -46,6 +46,11 @@ def lib() -> C.CDLL:
         L.tcgnn_spmm_f32.argtypes = [vp, vp, i64, vp, vp, i64, i32, vp]
         L.tcgnn_sddmm_f32.argtypes = [vp, vp, i64, vp, i32, vp]
         L.tcgnn_debug_umma.argtypes = [vp, i32, vp, i32, u64, u64, u32, i32, i32, i32, vp, i32, vp]
+        L.tcgnn_spmm_f32_ex.argtypes = [vp, vp, i64, vp, vp, i64, i32, u32, vp]
+        L.tcgnn_sddmm_f32_ex.argtypes = [vp, vp, i64, vp, i32, u32, vp]
+        L.tcgnn_round_tf32.argtypes = [vp, i64, vp, i64, i64, i32, vp]
+        for name in ("tcgnn_spmm_f32_ex", "tcgnn_sddmm_f32_ex", "tcgnn_round_tf32"):
+            getattr(L, name).restype = C.c_int
         L.tcgnn_debug_umma_bench.argtypes = [u64, u64, u32, i32, i32, i32, i32, i32, i32, i32, i32, C.POINTER(i64), vp]
         L.tcgnn_debug_umma_bench.restype = C.c_int
         for name in ("tcgnn_sgt_cpu", "tcgnn_sgt_cuda", "tcgnn_sgt_cuda_panel", "tcgnn_plan_create", "tcgnn_plan_create_panel", "tcgnn_plan_destroy", "tcgnn_plan_info",

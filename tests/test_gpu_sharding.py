@@ -122,3 +122,35 @@ def test_two_ranks_over_nccl():
         p.join(timeout=120)
         assert p.exitcode == 0
     assert all(ok for _, ok in res)
+
+
+def test_prerounded_operands_give_identical_results():
+    """tcgnn_round_tf32 + TCGNN_X_IS_TF32 (what the sharded path ships between GPUs) == rounding inside the op."""
+    import torch
+    import TCGNN
+    n = 6000
+    rp, ci = orc.rmat_graph(n, 150000, seed=31)
+    bp, e2c, e2r, _ = orc.sgt(rp, ci, n)
+    g = [torch.from_numpy(a).cuda() for a in (rp, ci, bp, e2c, e2r)]
+    x = torch.randn(n, 96, device="cuda", generator=torch.Generator(device="cuda").manual_seed(3))
+    xr = TCGNN.round_tf32(x)
+    assert torch.equal(xr, torch.from_numpy(orc.tf32_rna(x.cpu().numpy())).cuda())
+    # windows split over CTAs are combined with fp32 atomics (order varies run to run): compare the ops on
+    # integer-valued data, where every partial sum is exact
+    xi = torch.randint(-8, 9, (n, 96), device="cuda", generator=torch.Generator(device="cuda").manual_seed(4)).float()
+    xir = TCGNN.round_tf32(xi)
+    assert torch.equal(xir, xi)
+    y0 = TCGNN.forward(xi, *g)[0]
+    y1 = TCGNN.panel_forward(xir, 0, *g, x_is_tf32=True)[0]
+    assert torch.equal(y0, y1)
+    e0 = TCGNN.forward_ef(x, *g)[0]                     # SDDMM has no cross-CTA accumulation
+    e1 = TCGNN.panel_forward_ef(xr, 0, *g, x_is_tf32=True)[0]
+    assert torch.equal(e0, e1)
+    w = torch.randint(-3, 4, (1, len(ci)), device="cuda").float()
+    z0 = TCGNN.forward_AGNN(xi, g[0], g[1], w, *g[2:])[0]
+    z1 = TCGNN.panel_forward_AGNN(xir, 0, g[0], g[1], w, *g[2:], x_is_tf32=True)[0]
+    assert torch.equal(z0, z1)
+    # and on random-normal data within the accumulation-order tolerance
+    yr = TCGNN.panel_forward(xr, 0, *g, x_is_tf32=True)[0]
+    assert_normwise(yr.cpu().numpy(), orc.spmm(x.cpu().numpy(), rp, ci), orc.spmm_abs(x.cpu().numpy(), rp, ci), 1e-5,
+                    "pre-rounded SpMM")
