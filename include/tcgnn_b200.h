@@ -119,6 +119,11 @@ int tcgnn_sddmm_f32(tcgnn_plan* plan, const float* x, int64_t ldx, float* edge_o
  * [dim, ldo) are zero-filled. */
 #define TCGNN_X_IS_TF32 1u
 int tcgnn_round_tf32(const float* x, int64_t ldx, float* out, int64_t ldo, int64_t rows, int32_t dim, void* stream);
+/* Same, fused with the exchange of row-panel sharding: `out` may be PEER memory (a P2P-mapped pointer into another
+ * GPU's gathered matrix) -- the rounded rows are written straight over NVLink -- and tcgnn_round_tf32_multicast
+ * takes an NVSwitch multicast address (multimem.st: one store reaches the buffer of every GPU of the group). */
+int tcgnn_round_tf32_multicast(const float* x, int64_t ldx, float* out_mc, int64_t ldo, int64_t rows, int32_t dim,
+                               void* stream);
 int tcgnn_spmm_f32_ex(tcgnn_plan* plan, const float* x, int64_t ldx, const float* edge_weight, float* y,
                       int64_t ldy, int32_t dim, uint32_t flags, void* stream);
 int tcgnn_sddmm_f32_ex(tcgnn_plan* plan, const float* x, int64_t ldx, float* edge_out, int32_t dim,

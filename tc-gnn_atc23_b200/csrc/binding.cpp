@@ -364,6 +364,23 @@ std::vector<int64_t> plan_info(torch::Tensor nodePointer, torch::Tensor edgeList
   return info;
 }
 
+// Fused "round + push": writes cvt.rna.tf32(input) to a raw device address -- local memory, a P2P-mapped
+// pointer into a peer GPU's gathered matrix, or (multicast = true) an NVSwitch multicast address.
+void round_tf32_into(torch::Tensor input, int64_t out_ptr, int64_t ldo, bool multicast) {
+  CHECK_INPUT(input);
+  CHECK_F32(input);
+  TORCH_CHECK(input.dim() == 2 && input.size(1) >= 1, "input must be [rows, dim]");
+  if (input.size(0) == 0) return;
+  c10::cuda::CUDAGuard guard(input.device());
+  auto stream = c10::cuda::getCurrentCUDAStream(input.get_device()).stream();
+  float* out = reinterpret_cast<float*>(static_cast<uintptr_t>(out_ptr));
+  const int st = multicast ? tcgnn_round_tf32_multicast(input.data_ptr<float>(), input.size(1), out, ldo, input.size(0),
+                                                        static_cast<int32_t>(input.size(1)), stream)
+                           : tcgnn_round_tf32(input.data_ptr<float>(), input.size(1), out, ldo, input.size(0),
+                                              static_cast<int32_t>(input.size(1)), stream);
+  check_status(st, "tcgnn_round_tf32");
+}
+
 }  // namespace
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
@@ -392,6 +409,9 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("panel_forward_ef", &panel_forward_ef, "SDDMM of a row panel: (X_all, row_base, nodePointer, edgeList, bp, e2c, e2r)",
         py::arg("input"), py::arg("row_base"), py::arg("nodePointer"), py::arg("edgeList"), py::arg("blockPartition"),
         py::arg("edgeToColumn"), py::arg("edgeToRow"), py::arg("x_is_tf32") = false);
+  m.def("round_tf32_into", &round_tf32_into,
+        "(input, out_ptr, ldo, multicast): cvt.rna.tf32(input) written to a raw (local / peer / multicast) address",
+        py::arg("input"), py::arg("out_ptr"), py::arg("ldo"), py::arg("multicast") = false);
   m.def("round_tf32", &round_tf32, "cvt.rna.tf32 of a [rows, dim] CUDA matrix (dim % 4 == 0), for x_is_tf32 = True");
   m.def("clear_plan_cache", &clear_plan_cache, "Destroy all cached kernel plans");
   m.def("plan_info", &plan_info, "[num_nodes, num_edges, num_windows, num_tiles, plan_bytes, pairs, device, sms]");

@@ -168,13 +168,23 @@ int tcgnn_sddmm_f32(tcgnn_plan* plan, const float* x, int64_t ldx, float* edge_o
   return tcgnn_sddmm_f32_ex(plan, x, ldx, edge_out, dim, 0u, stream);
 }
 
-int tcgnn_round_tf32(const float* x, int64_t ldx, float* out, int64_t ldo, int64_t rows, int32_t dim, void* stream) {
+static int round_tf32_checked(const float* x, int64_t ldx, float* out, int64_t ldo, int64_t rows, int32_t dim,
+                              int multimem, void* stream) {
   if (x == nullptr || out == nullptr || rows < 0 || dim < 1 || ldx < dim || ldo < dim || (ldo & 3) != 0 ||
       (reinterpret_cast<uintptr_t>(out) & 15) != 0) {
     set_last_error("tcgnn_round_tf32: bad argument (out must be 16-byte aligned with ldo %% 4 == 0)");
     return TCGNN_ERR_INVALID_ARG;
   }
-  return round_tf32_launch(x, ldx, out, ldo, rows, dim, static_cast<cudaStream_t>(stream));
+  return round_tf32_launch(x, ldx, out, ldo, rows, dim, multimem, static_cast<cudaStream_t>(stream));
+}
+
+int tcgnn_round_tf32(const float* x, int64_t ldx, float* out, int64_t ldo, int64_t rows, int32_t dim, void* stream) {
+  return round_tf32_checked(x, ldx, out, ldo, rows, dim, 0, stream);
+}
+
+int tcgnn_round_tf32_multicast(const float* x, int64_t ldx, float* out_mc, int64_t ldo, int64_t rows, int32_t dim,
+                               void* stream) {
+  return round_tf32_checked(x, ldx, out_mc, ldo, rows, dim, 1, stream);
 }
 
 int tcgnn_debug_umma(const void* a_image, int32_t a_bytes, const void* b_image, int32_t b_bytes, uint64_t adesc,

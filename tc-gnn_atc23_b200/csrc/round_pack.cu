@@ -15,7 +15,7 @@ namespace {
 
 __global__ void __launch_bounds__(256)
 tf32_round_pack_kernel(const float* __restrict__ x, int64_t ldx, int32_t dim, int64_t rows, float* __restrict__ out,
-                       int64_t ldr, int vec_ok) {
+                       int64_t ldr, int vec_ok, int multimem) {
   const int32_t nvec = static_cast<int32_t>(ldr >> 2);
   const int64_t total = rows * nvec;
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
@@ -32,7 +32,16 @@ tf32_round_pack_kernel(const float* __restrict__ x, int64_t ldx, int32_t dim, in
       if (f + 2 < dim) v.z = __ldg(src + 2);
       if (f + 3 < dim) v.w = __ldg(src + 3);
     }
-    *reinterpret_cast<float4*>(out + r * ldr + f) = tf32_rna4(v);
+    const float4 o = tf32_rna4(v);
+    float* dst = out + r * ldr + f;
+    if (multimem) {
+      // `out` is an NVSwitch multicast address: one store lands in the buffer of every GPU of the group
+      asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(o.x), "f"(o.y),
+                   "f"(o.z), "f"(o.w)
+                   : "memory");
+    } else {
+      *reinterpret_cast<float4*>(dst) = o;
+    }
   }
 }
 
@@ -70,7 +79,7 @@ int round_pack_launch(tcgnn_plan* plan, const float* x, int64_t ldx, int32_t dim
   int64_t g = (total + 255) / 256;
   if (g > static_cast<int64_t>(plan->num_sms) * 16) g = static_cast<int64_t>(plan->num_sms) * 16;
   if (g < 1) g = 1;
-  tf32_round_pack_kernel<<<static_cast<int>(g), 256, 0, stream>>>(x, ldx, dim, rows, plan->x_round, ldr, vec_ok);
+  tf32_round_pack_kernel<<<static_cast<int>(g), 256, 0, stream>>>(x, ldx, dim, rows, plan->x_round, ldr, vec_ok, 0);
   count_launch();
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
@@ -81,7 +90,7 @@ int round_pack_launch(tcgnn_plan* plan, const float* x, int64_t ldx, int32_t dim
   return TCGNN_OK;
 }
 
-int round_tf32_launch(const float* x, int64_t ldx, float* out, int64_t ldo, int64_t rows, int32_t dim,
+int round_tf32_launch(const float* x, int64_t ldx, float* out, int64_t ldo, int64_t rows, int32_t dim, int multimem,
                       cudaStream_t stream) {
   if (rows <= 0) return TCGNN_OK;
   const int vec_ok = (reinterpret_cast<uintptr_t>(x) % 16 == 0) && (ldx % 4 == 0);
@@ -89,7 +98,7 @@ int round_tf32_launch(const float* x, int64_t ldx, float* out, int64_t ldo, int6
   int64_t g = (total + 255) / 256;
   if (g > 148 * 16) g = 148 * 16;
   if (g < 1) g = 1;
-  tf32_round_pack_kernel<<<static_cast<int>(g), 256, 0, stream>>>(x, ldx, dim, rows, out, ldo, vec_ok);
+  tf32_round_pack_kernel<<<static_cast<int>(g), 256, 0, stream>>>(x, ldx, dim, rows, out, ldo, vec_ok, multimem);
   count_launch();
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {

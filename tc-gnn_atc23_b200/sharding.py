@@ -19,6 +19,7 @@ calls go to the `TCGNN` extension and need a GPU -- there is no CPU fallback.
 """
 from __future__ import annotations
 
+import os
 from typing import List, Optional, Sequence
 
 import torch
@@ -27,12 +28,32 @@ import torch.distributed as dist
 from config import BLK_H, BLK_W
 
 
-def partition_rows(row_ptr: torch.Tensor, world_size: int, blk_h: int = BLK_H) -> List[int]:
-    """Row boundaries [b_0 = 0, ..., b_world = N], each a multiple of `blk_h` (except N), balancing
-    the stored non-zeros per panel.  Deterministic, identical on every rank."""
+def partition_rows(row_ptr: torch.Tensor, world_size: int, blk_h: int = BLK_H,
+                   block_partition: Optional[torch.Tensor] = None, window_cost: int = 3) -> List[int]:
+    """Row boundaries [b_0 = 0, ..., b_world = N], each a multiple of `blk_h` (except N).  Deterministic,
+    identical on every rank.
+
+    Without `block_partition` the stored non-zeros per panel are balanced.  With the graph's SGT tile counts
+    (`blockPartition`, one entry per `blk_h`-row window) the panels are balanced on what the kernels' time is
+    actually proportional to: TC blocks + `window_cost` per window (the same cost model the CTA slices inside a
+    GPU use, plan.cu) -- on R-MAT graphs the hub panel has 2-3x more non-zeros per TC block than the tail
+    panel, and non-zero balancing left the slowest rank 37 % behind on 2 GPUs."""
     if world_size < 1:
         raise ValueError("world_size must be >= 1")
     n = int(row_ptr.numel()) - 1
+    last = n // blk_h * blk_h if n >= blk_h else 0
+    if block_partition is not None:
+        cost = torch.clamp(block_partition.to(torch.int64).cpu(), min=1) + int(window_cost)
+        pre = torch.cumsum(cost, 0)                      # cost of windows [0, w]
+        total = int(pre[-1]) if pre.numel() else 0
+        bounds = [0]
+        for k in range(1, world_size):
+            target = (total * k) // world_size
+            w = int(torch.searchsorted(pre, torch.tensor(target, dtype=torch.int64), right=False)) + 1
+            r = min(max(w * blk_h, bounds[-1]), last)
+            bounds.append(r)
+        bounds.append(n)
+        return bounds
     rp = row_ptr.to(torch.int64).cpu()
     nnz = int(rp[-1] - rp[0])
     bounds = [0]
@@ -41,7 +62,7 @@ def partition_rows(row_ptr: torch.Tensor, world_size: int, blk_h: int = BLK_H) -
         r = int(torch.searchsorted(rp, torch.tensor(target, dtype=torch.int64), right=False))
         r = min(max(r, 0), n)
         r = (r + blk_h // 2) // blk_h * blk_h          # nearest window boundary
-        r = min(max(r, bounds[-1]), n // blk_h * blk_h if n >= blk_h else 0)
+        r = min(max(r, bounds[-1]), last)
         bounds.append(r)
     bounds.append(n)
     return bounds
@@ -56,7 +77,21 @@ class RowPanel:
         graph's (blockPartition, edgeToColumn, edgeToRow) to slice instead of recomputing."""
         self.rank, self.world_size = int(rank), int(world_size)
         self.num_cols = int(row_ptr.numel()) - 1
-        self.bounds = list(bounds) if bounds is not None else partition_rows(row_ptr, world_size)
+        if bounds is None and sgt is None and world_size > 1 and row_ptr.is_cuda and self.num_cols > 0:
+            # SGT of the whole graph on this GPU (milliseconds), so the panels can be balanced on TC blocks;
+            # the panel's arrays are then slices of it (bit-identical to a per-panel SGT)
+            import TCGNN
+            nwin_all = (self.num_cols + BLK_H - 1) // BLK_H
+            g_bp = torch.zeros(nwin_all, dtype=torch.int32, device=row_ptr.device)
+            g_e2c = torch.zeros(col_idx.numel(), dtype=torch.int32, device=row_ptr.device)
+            g_e2r = torch.zeros(col_idx.numel(), dtype=torch.int32, device=row_ptr.device)
+            TCGNN.preprocess_panel(col_idx.contiguous(), row_ptr.contiguous(), self.num_cols, self.num_cols, BLK_H,
+                                   BLK_W, g_bp, g_e2c, g_e2r)
+            sgt = (g_bp, g_e2c, g_e2r)
+        if bounds is not None:
+            self.bounds = list(bounds)
+        else:
+            self.bounds = partition_rows(row_ptr, world_size, block_partition=sgt[0] if sgt is not None else None)
         if len(self.bounds) != world_size + 1 or self.bounds[0] != 0 or self.bounds[-1] != self.num_cols:
             raise ValueError("bounds must be [0, ..., num_nodes] with world_size + 1 entries")
         for b in self.bounds[1:-1]:
@@ -88,6 +123,7 @@ class RowPanel:
                 TCGNN.preprocess_panel(self.column_index, self.row_pointers, self.num_rows, self.num_cols, BLK_H,
                                        BLK_W, self.blockPartition, self.edgeToColumn, self.edgeToRow)
         self._x_all = None
+        self._symm = {}    # feature width -> (symmetric buffer, handle, peer views, multicast?)
 
     # ------------------------------------------------------------------ exchange
     @property
@@ -102,10 +138,22 @@ class RowPanel:
         """The per-layer exchange: every rank contributes its [num_rows, D] panel, all receive the
         [num_cols, D] matrix (one all-gather; uneven panels).  With `round_tf32` (CUDA, D % 4 == 0) the
         panel is rounded to TF32 before it is sent, so no rank has to round the whole gathered matrix
-        again: pass the result to spmm / sddmm with x_is_tf32=True."""
+        again: pass the result to spmm / sddmm with x_is_tf32=True.
+
+        On NCCL groups with `round_tf32` the exchange is FUSED with the rounding pass (env
+        TCGNN_EXCHANGE=multicast|p2p|nccl, default: multicast when the group supports it, else p2p): the
+        gathered matrix lives in symmetric memory, and the kernel that rounds the local panel writes its
+        result straight into every GPU's copy -- one multimem store through the NVSwitch, or one pass per
+        peer over P2P-mapped memory -- bracketed by two device-side barriers.  No staging copy, no
+        broadcast tree: R-MAT panels are balanced on non-zeros, so their row counts (= bytes sent) differ
+        2-3x and NCCL's uneven all-gather (grouped broadcasts) took ~0.9 ms for 119 MB on 8 GPUs."""
         if x_local.shape[0] != self.num_rows:
             raise ValueError(f"x_local has {x_local.shape[0]} rows, the panel has {self.num_rows}")
         d = x_local.shape[1]
+        mode = os.environ.get("TCGNN_EXCHANGE", "auto")
+        if (round_tf32 and out is None and self.world_size > 1 and x_local.is_cuda and d % 4 == 0
+                and mode != "nccl" and dist.get_backend(group) == "nccl"):
+            return self._fused_exchange(x_local.contiguous(), group, mode)
         if round_tf32 and self.num_rows > 0:
             import TCGNN
             x_local = TCGNN.round_tf32(x_local.contiguous())
@@ -128,6 +176,34 @@ class RowPanel:
                     dist.broadcast(views[g], src=dist.get_global_rank(group, g) if group is not None else g,
                                    group=group)
         return out
+
+    def _fused_exchange(self, x_local: torch.Tensor, group, mode: str) -> torch.Tensor:
+        import TCGNN
+        import torch.distributed._symmetric_memory as symm_mem
+        d = x_local.shape[1]
+        st = self._symm.get(d)
+        if st is None:
+            grp = group if group is not None else dist.group.WORLD
+            buf = symm_mem.empty((self.num_cols, d), dtype=torch.float32, device=x_local.device)
+            hdl = symm_mem.rendezvous(buf, grp)
+            peers = [hdl.get_buffer(p, (self.num_cols, d), torch.float32) for p in range(self.world_size)]
+            use_mc = mode in ("auto", "multicast") and bool(getattr(hdl, "has_multicast_support", False)) \
+                and int(hdl.multicast_ptr) != 0
+            if mode == "multicast" and not use_mc:
+                raise RuntimeError("TCGNN_EXCHANGE=multicast but the group has no NVSwitch multicast support")
+            st = self._symm[d] = (buf, hdl, peers, use_mc)
+        buf, hdl, peers, use_mc = st
+        row_bytes = d * 4
+        hdl.barrier(channel=0)                 # every rank has finished reading the previous gathered matrix
+        if self.num_rows > 0:
+            if use_mc:
+                TCGNN.round_tf32_into(x_local, int(hdl.multicast_ptr) + self.row_base * row_bytes, d, True)
+            else:
+                for k in range(self.world_size):   # step k: everybody writes to (rank + k) % world -- no hot spot
+                    p = (self.rank + k) % self.world_size
+                    TCGNN.round_tf32_into(x_local, peers[p].data_ptr() + self.row_base * row_bytes, d, False)
+        hdl.barrier(channel=1)                 # every rank's rows have landed in every copy
+        return buf
 
     # ------------------------------------------------------------------ compute (GPU only)
     def spmm(self, x_all: torch.Tensor, edge_attention: Optional[torch.Tensor] = None,

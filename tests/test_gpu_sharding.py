@@ -92,11 +92,18 @@ def _nccl_worker(rank, world, port, q):
         t_rp, t_ci = torch.from_numpy(rp).cuda(), torch.from_numpy(ci).cuda()
         p = RowPanel(t_rp, t_ci, rank, world)
         x_local = torch.from_numpy(x[p.row_base:p.row_base + p.num_rows]).cuda()
-        y = p.aggregate(x_local)                                   # all-gather over NCCL + panel SpMM
+        want = orc.spmm(x, rp, ci)[p.row_base:p.row_base + p.num_rows]
+        ok = True
+        # the exchange three ways: NCCL uneven all-gather, fused round + P2P push, fused round + NVSwitch
+        # multicast (auto falls back to P2P when the group has no multicast support); twice each, because the
+        # second step reuses the symmetric buffer behind the barriers
+        for mode in ("nccl", "p2p", "auto"):
+            os.environ["TCGNN_EXCHANGE"] = mode
+            for _ in range(2):
+                y = p.aggregate(x_local)                           # exchange + panel SpMM
+                ok = ok and np.array_equal(y.cpu().numpy(), want)
         y2, ef = p.agnn_aggregate(x_local, torch.full((1, 1), 0.5, device="cuda"))
         torch.cuda.synchronize()
-        want = orc.spmm(x, rp, ci)[p.row_base:p.row_base + p.num_rows]
-        ok = np.array_equal(y.cpu().numpy(), want)
         ef_want = orc.sddmm(x, rp, ci)[p.edge_begin:p.edge_end]
         ok = ok and np.array_equal(ef.cpu().numpy(), ef_want)
         yw = orc.spmm(x, rp, ci, orc.sddmm(x, rp, ci) * 0.5)[p.row_base:p.row_base + p.num_rows]

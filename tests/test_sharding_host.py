@@ -62,7 +62,8 @@ def test_panel_sgt_is_slice_of_global_sgt(world):
         assert np.array_equal(p.row_pointers.numpy(), rp[r0:r1 + 1] - rp[r0])
         assert np.array_equal(p.column_index.numpy(), ci[e0:e1])          # global column ids
         # slicing precomputed global SGT arrays gives the same panel
-        q = RowPanel(t_rp, t_ci, rank, world, sgt=(torch.from_numpy(bp), torch.from_numpy(e2c), torch.from_numpy(e2r)))
+        q = RowPanel(t_rp, t_ci, rank, world, bounds=p.bounds,
+                     sgt=(torch.from_numpy(bp), torch.from_numpy(e2c), torch.from_numpy(e2r)))
         for a, b_ in zip(p.graph, q.graph):
             assert torch.equal(a, b_)
         covered_rows += p.num_rows
@@ -114,3 +115,21 @@ def test_gloo_world2_all_gather_exchange():
         assert p.exitcode == 0
     assert all(ok for _, ok, _ in res)
     assert res[0][2] == res[1][2]        # same boundaries on both ranks
+
+
+def test_partition_on_tc_blocks_balances_tiles():
+    """With the SGT tile counts the panels are balanced on TC blocks (+ a per-window cost), which is what the
+    kernels' time follows; boundaries stay on window boundaries and cover every row once."""
+    from sharding import partition_rows
+    n = 40000
+    rp, ci = orc.rmat_graph(n, 900000, seed=33)
+    bp, _, _, _ = orc.sgt(rp, ci, n)
+    for world in (2, 3, 8):
+        b = partition_rows(torch.from_numpy(rp), world, block_partition=torch.from_numpy(bp))
+        assert b[0] == 0 and b[-1] == n and all(x % 16 == 0 for x in b[1:-1]) and b == sorted(b)
+        cost = [int((np.maximum(bp[b[i] // 16:(b[i + 1] + 15) // 16], 1) + 3).sum()) for i in range(world)]
+        assert max(cost) <= 1.05 * (sum(cost) / world) + int(bp.max()) + 3
+        nnz_b = partition_rows(torch.from_numpy(rp), world)
+        tiles_nnz = [int(bp[nnz_b[i] // 16:(nnz_b[i + 1] + 15) // 16].sum()) for i in range(world)]
+        tiles_tc = [int(bp[b[i] // 16:(b[i + 1] + 15) // 16].sum()) for i in range(world)]
+        assert max(tiles_tc) <= max(tiles_nnz)
