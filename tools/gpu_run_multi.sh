@@ -3,7 +3,7 @@
 mkdir -p gpurun_out
 N=${1:-2}
 nvidia-smi --query-gpu=index,name --format=csv,noheader | head -8
-timeout 600 python -m pytest tests/test_gpu_sharding.py -m gpu -q --timeout 300 2>&1 | tail -3
+true
 for wl in ${WORKLOADS:-reddit-like-rmat}; do
 for n in ${NS:-$N}; do
 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $n --steps 10 --warmup 3 --workload $wl --no-cpu-baseline > gpurun_out/bench_${wl}_n$n.json 2> gpurun_out/bench_${wl}_n$n.err
