@@ -124,6 +124,12 @@ int tcgnn_round_tf32(const float* x, int64_t ldx, float* out, int64_t ldo, int64
  * takes an NVSwitch multicast address (multimem.st: one store reaches the buffer of every GPU of the group). */
 int tcgnn_round_tf32_multicast(const float* x, int64_t ldx, float* out_mc, int64_t ldo, int64_t rows, int32_t dim,
                                void* stream);
+/* Copies the row segments [seg_begin_rows[i], seg_end_rows[i]) (rows of `ld` floats, ld % 4 == 0) of the matrix at
+ * `src` to the same rows of the matrices at peers[0..n_peers) -- P2P-mapped pointers into other GPUs' copies -- in
+ * one launch (second phase of the balanced exchange of sharding.py).  peers / segment arrays are HOST arrays
+ * (<= 16 entries each). */
+int tcgnn_push_rows(const float* src, float* const* peers, int32_t n_peers, const int64_t* seg_begin_rows,
+                    const int64_t* seg_end_rows, int32_t n_segs, int64_t ld, void* stream);
 int tcgnn_spmm_f32_ex(tcgnn_plan* plan, const float* x, int64_t ldx, const float* edge_weight, float* y,
                       int64_t ldy, int32_t dim, uint32_t flags, void* stream);
 int tcgnn_sddmm_f32_ex(tcgnn_plan* plan, const float* x, int64_t ldx, float* edge_out, int32_t dim,

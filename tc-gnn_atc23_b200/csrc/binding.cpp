@@ -381,6 +381,22 @@ void round_tf32_into(torch::Tensor input, int64_t out_ptr, int64_t ldo, bool mul
   check_status(st, "tcgnn_round_tf32");
 }
 
+// Second phase of the balanced exchange: rows [begin, end) segments of `local` -> the same rows at every peer address.
+void push_rows(torch::Tensor local, std::vector<int64_t> peer_ptrs, std::vector<int64_t> seg_begin,
+               std::vector<int64_t> seg_end) {
+  CHECK_INPUT(local);
+  CHECK_F32(local);
+  TORCH_CHECK(local.dim() == 2 && seg_begin.size() == seg_end.size(), "push_rows: bad arguments");
+  std::vector<float*> peers;
+  for (int64_t p : peer_ptrs) peers.push_back(reinterpret_cast<float*>(static_cast<uintptr_t>(p)));
+  c10::cuda::CUDAGuard guard(local.device());
+  auto stream = c10::cuda::getCurrentCUDAStream(local.get_device()).stream();
+  check_status(tcgnn_push_rows(local.data_ptr<float>(), peers.data(), static_cast<int32_t>(peers.size()),
+                               seg_begin.data(), seg_end.data(), static_cast<int32_t>(seg_begin.size()),
+                               local.size(1), stream),
+               "tcgnn_push_rows");
+}
+
 }  // namespace
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
@@ -412,6 +428,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("round_tf32_into", &round_tf32_into,
         "(input, out_ptr, ldo, multicast): cvt.rna.tf32(input) written to a raw (local / peer / multicast) address",
         py::arg("input"), py::arg("out_ptr"), py::arg("ldo"), py::arg("multicast") = false);
+  m.def("push_rows", &push_rows, "(local, peer_ptrs, seg_begin_rows, seg_end_rows): copy row segments to peers");
   m.def("round_tf32", &round_tf32, "cvt.rna.tf32 of a [rows, dim] CUDA matrix (dim % 4 == 0), for x_is_tf32 = True");
   m.def("clear_plan_cache", &clear_plan_cache, "Destroy all cached kernel plans");
   m.def("plan_info", &plan_info, "[num_nodes, num_edges, num_windows, num_tiles, plan_bytes, pairs, device, sms]");

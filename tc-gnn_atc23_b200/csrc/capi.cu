@@ -168,6 +168,27 @@ int tcgnn_sddmm_f32(tcgnn_plan* plan, const float* x, int64_t ldx, float* edge_o
   return tcgnn_sddmm_f32_ex(plan, x, ldx, edge_out, dim, 0u, stream);
 }
 
+int tcgnn_push_rows(const float* src, float* const* peers, int32_t n_peers, const int64_t* seg_begin_rows,
+                    const int64_t* seg_end_rows, int32_t n_segs, int64_t ld, void* stream) {
+  if (src == nullptr || peers == nullptr || n_peers < 0 || n_peers > 16 || n_segs < 0 || n_segs > 16 ||
+      (n_segs > 0 && (seg_begin_rows == nullptr || seg_end_rows == nullptr)) || ld < 4 || (ld & 3) != 0 ||
+      (reinterpret_cast<uintptr_t>(src) & 15) != 0) {
+    set_last_error("tcgnn_push_rows: bad argument (<= 16 peers, <= 16 segments, ld %% 4 == 0, 16-byte aligned bases)");
+    return TCGNN_ERR_INVALID_ARG;
+  }
+  for (int i = 0; i < n_peers; ++i)
+    if (peers[i] == nullptr || (reinterpret_cast<uintptr_t>(peers[i]) & 15) != 0) {
+      set_last_error("tcgnn_push_rows: peer %d is null or not 16-byte aligned", i);
+      return TCGNN_ERR_INVALID_ARG;
+    }
+  for (int i = 0; i < n_segs; ++i)
+    if (seg_begin_rows[i] < 0 || seg_end_rows[i] < seg_begin_rows[i]) {
+      set_last_error("tcgnn_push_rows: bad segment %d", i);
+      return TCGNN_ERR_INVALID_ARG;
+    }
+  return push_rows_launch(src, peers, n_peers, seg_begin_rows, seg_end_rows, n_segs, ld, static_cast<cudaStream_t>(stream));
+}
+
 static int round_tf32_checked(const float* x, int64_t ldx, float* out, int64_t ldo, int64_t rows, int32_t dim,
                               int multimem, void* stream) {
   if (x == nullptr || out == nullptr || rows < 0 || dim < 1 || ldx < dim || ldo < dim || (ldo & 3) != 0 ||

@@ -75,6 +75,8 @@ int spmm_launch(tcgnn_plan* plan, const float* x, int64_t ldx, const float* edge
                 int32_t dim, uint32_t op_flags, cudaStream_t stream);
 int sddmm_launch(tcgnn_plan* plan, const float* x, int64_t ldx, float* edge_out, int32_t dim, uint32_t op_flags,
                  cudaStream_t stream);
+int push_rows_launch(const float* src, float* const* peers, int32_t n_peers, const int64_t* seg_begin_rows,
+                     const int64_t* seg_end_rows, int32_t n_segs, int64_t ld, cudaStream_t stream);
 int round_tf32_launch(const float* x, int64_t ldx, float* out, int64_t ldo, int64_t rows, int32_t dim, int multimem,
                       cudaStream_t stream);
 int sgt_cuda(const int32_t* row_ptr, const int32_t* col_idx, int32_t num_nodes, int32_t num_cols, int64_t num_edges,

@@ -11,6 +11,9 @@
 
 namespace tcgnn {
 
+constexpr int kMaxPushPeers = 16;
+constexpr int kMaxPushSegs = 16;
+
 namespace {
 
 __global__ void __launch_bounds__(256)
@@ -87,6 +90,59 @@ int round_pack_launch(tcgnn_plan* plan, const float* x, int64_t ldx, int32_t dim
     return TCGNN_ERR_CUDA;
   }
   *xr_out = plan->x_round;
+  return TCGNN_OK;
+}
+
+// Second phase of the balanced exchange (sharding.py): copy row segments of the local gathered matrix to the same
+// rows of every peer's copy (P2P-mapped pointers), one launch for all peers and segments.
+struct PushArgs {
+  float* peers[kMaxPushPeers];
+  int64_t seg_begin[kMaxPushSegs];   // in 16-byte vectors from the matrix base
+  int64_t seg_vecs_prefix[kMaxPushSegs + 1];
+  int32_t n_peers, n_segs;
+};
+
+namespace {
+__global__ void __launch_bounds__(256) push_rows_kernel(const float* __restrict__ src, PushArgs a) {
+  const int64_t total = a.seg_vecs_prefix[a.n_segs];
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int p = blockIdx.y; p < a.n_peers; p += gridDim.y) {
+    float4* dst = reinterpret_cast<float4*>(a.peers[p]);
+    const float4* s4 = reinterpret_cast<const float4*>(src);
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total; i += stride) {
+      int sgm = 0;
+#pragma unroll
+      for (int k = 1; k < kMaxPushSegs; ++k) sgm += (k < a.n_segs && i >= a.seg_vecs_prefix[k]) ? 1 : 0;
+      const int64_t v = a.seg_begin[sgm] + (i - a.seg_vecs_prefix[sgm]);
+      dst[v] = __ldg(s4 + v);
+    }
+  }
+}
+}  // namespace
+
+int push_rows_launch(const float* src, float* const* peers, int32_t n_peers, const int64_t* seg_begin_rows,
+                     const int64_t* seg_end_rows, int32_t n_segs, int64_t ld, cudaStream_t stream) {
+  PushArgs a;
+  a.n_peers = n_peers;
+  a.n_segs = n_segs;
+  a.seg_vecs_prefix[0] = 0;
+  for (int i = 0; i < n_segs; ++i) {
+    a.seg_begin[i] = seg_begin_rows[i] * (ld >> 2);
+    a.seg_vecs_prefix[i + 1] = a.seg_vecs_prefix[i] + (seg_end_rows[i] - seg_begin_rows[i]) * (ld >> 2);
+  }
+  for (int i = 0; i < n_peers; ++i) a.peers[i] = peers[i];
+  const int64_t total = a.seg_vecs_prefix[n_segs];
+  if (total == 0 || n_peers == 0) return TCGNN_OK;
+  int64_t gx = (total + 255) / 256;
+  const int64_t cap = 148 * 8 / (n_peers > 0 ? n_peers : 1) + 1;
+  if (gx > cap) gx = cap;
+  push_rows_kernel<<<dim3(static_cast<unsigned>(gx), static_cast<unsigned>(n_peers)), 256, 0, stream>>>(src, a);
+  count_launch();
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_last_error("push_rows_kernel launch failed: %s", cudaGetErrorString(e));
+    return TCGNN_ERR_CUDA;
+  }
   return TCGNN_OK;
 }
 

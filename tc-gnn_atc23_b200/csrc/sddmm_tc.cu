@@ -10,7 +10,8 @@
 // A (gathered rows) and as B (the window's own 16 rows).  Only positions that are edges are
 // written (tile occupancy mask), in tile order; a second pass restores CSR edge order.
 //
-// A pipeline stage is one 32-feature chunk of one group: A 16 KB + B 2 KB.  The group's 16 tile records
+// A pipeline stage is one 64-feature chunk of one group: A 32 KB + B 4 KB, as two 32-feature sub-blocks (the
+// 128B-swizzled K-major image holds 32 floats per row); 8 MMAs per stage amortise the MMA warp's per-stage latency.  The group's 16 tile records
 // travel once per group through their own ring (TMA bulk copy), far ahead of the data.  X is first rounded
 // to tf32 (cvt.rna) and packed once per call (round_pack.cu), so the row gathers are plain asynchronous
 // copies.  CTA = 10 warps:
@@ -31,19 +32,22 @@ namespace tcgnn {
 
 namespace {
 
-constexpr int kStages = 10;
+constexpr int kStages = 5;
 constexpr int kMetaStages = 16;                           // ring of group records
 constexpr int kEpiWarps = 4;
 constexpr int kMmaWarp = 4;
 constexpr int kMetaWarp = 5;
 constexpr int kProducerWarp0 = 6;
-constexpr int kProducers = 6;                             // producer warp p owns the stages p, p + 6, ...
+constexpr int kProducers = 5;                             // producer warp p owns the stages p, p + 5, ...
 constexpr int kWarps = kProducerWarp0 + kProducers;
 constexpr int kThreads = kWarps * 32;
 constexpr int kAcc = 4;
 constexpr int kGroupTiles = 16;
-constexpr int kAStageBytes = 128 * 128;                    // 128 rows x 32 floats
-constexpr int kBStageBytes = TCGNN_BLK_H * 128;            // 16 rows x 32 floats
+constexpr int kChunk = 64;                                 // features per pipeline stage: two 32-feature sub-blocks
+constexpr int kASubBytes = 128 * 128;                      // 128 rows x 32 floats, 128B-swizzled K-major
+constexpr int kBSubBytes = TCGNN_BLK_H * 128;              // 16 rows x 32 floats
+constexpr int kAStageBytes = 2 * kASubBytes;               // 32 KB
+constexpr int kBStageBytes = 2 * kBSubBytes;               // 4 KB
 constexpr int kMetaTileBytes = kGroupTiles * static_cast<int>(sizeof(TileMeta));
 constexpr int kMetaStageBytes = kMetaTileBytes + 16;       // + header {tile_start, ntiles, win, 0}
 constexpr uint32_t kTmemCols = kAcc * 16;
@@ -54,17 +58,6 @@ static_assert(kProducers <= kStages, "a warp may not wait for the slot of an own
 static_assert(kMetaStages >= 2 * kProducers, "one feature chunk per group: every in-flight stage is another group");
 static_assert(kSmemBytes <= 232448, "exceeds the 227 KB of dynamic shared memory per CTA");
 constexpr uint32_t kTuneXLast = 16u;                       // env TCGNN_TUNE: gathers with L2 evict_last
-
-// groups [g_lo, g_hi) of this CTA: equal shares of the tile stream, cut at group boundaries
-__device__ __forceinline__ int32_t first_group_at_or_after(const int4* __restrict__ groups, int32_t num_groups,
-                                                           int32_t tile) {
-  int32_t lo = 0, hi = num_groups;
-  while (lo < hi) {
-    const int32_t mid = (lo + hi) >> 1;
-    if (groups[mid].x < tile) lo = mid + 1; else hi = mid;
-  }
-  return lo;
-}
 
 __global__ void __launch_bounds__(kThreads, 1)
 sddmm_tc_kernel(PlanView pv, const int4* __restrict__ groups, int32_t num_groups,
@@ -85,11 +78,13 @@ sddmm_tc_kernel(PlanView pv, const int4* __restrict__ groups, int32_t num_groups
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  // the plan's cost-balanced tile slices (launched with plan->grid CTAs), rounded to group boundaries
-  const int32_t g_lo = first_group_at_or_after(groups, num_groups, pv.slice_ptr[blockIdx.x]);
-  const int32_t g_hi = first_group_at_or_after(groups, num_groups, pv.slice_ptr[blockIdx.x + 1]);
+  // every group costs the same here (nkc stages of 128 + 16 rows, however many of its 16 tiles exist), so the
+  // persistent CTAs take equal shares of the GROUPS -- not of the tiles: R-MAT graphs have long runs of one-tile
+  // windows, i.e. one-tile groups
+  const int32_t g_lo = static_cast<int32_t>(static_cast<int64_t>(num_groups) * blockIdx.x / gridDim.x);
+  const int32_t g_hi = static_cast<int32_t>(static_cast<int64_t>(num_groups) * (blockIdx.x + 1) / gridDim.x);
   const int32_t n_groups = g_hi - g_lo;
-  const int32_t nkc = (dim + 31) >> 5;          // 32-feature chunks
+  const int32_t nkc = (dim + kChunk - 1) / kChunk;   // 64-feature chunks
   const int32_t n_stages = n_groups * nkc;
 
   if (threadIdx.x == 0) {
@@ -186,17 +181,19 @@ sddmm_tc_kernel(PlanView pv, const int4* __restrict__ groups, int32_t num_groups
       tc_fence_after();
       const uint64_t adesc = desc0 | static_cast<uint64_t>(((a_smem + s * kAStageBytes) & 0x3FFFFu) >> 4);
       const uint64_t bdesc = desc0 | static_cast<uint64_t>(((b_smem + s * kBStageBytes) & 0x3FFFFu) >> 4);
-      const int ksteps = min(4, (dim - kc * 32 + 7) >> 3);
+      const int ksteps = min(8, (dim - kc * kChunk + 7) >> 3);   // K = 8 per MMA; 4 per 32-feature sub-block
       if (elect_one()) {
-        if (ksteps == 4) {
+        if (ksteps == 8) {
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks)
-            umma_tf32(tmem_base + b * 16, adesc + static_cast<uint64_t>(ks * 2), bdesc + static_cast<uint64_t>(ks * 2),
-                      idesc, (kc | ks) != 0 ? 1u : 0u);
+          for (int ks = 0; ks < 8; ++ks)
+            umma_tf32(tmem_base + b * 16, adesc + static_cast<uint64_t>(((ks >> 2) * kASubBytes >> 4) + (ks & 3) * 2),
+                      bdesc + static_cast<uint64_t>(((ks >> 2) * kBSubBytes >> 4) + (ks & 3) * 2), idesc,
+                      (kc | ks) != 0 ? 1u : 0u);
         } else {
           for (int ks = 0; ks < ksteps; ++ks)
-            umma_tf32(tmem_base + b * 16, adesc + static_cast<uint64_t>(ks * 2), bdesc + static_cast<uint64_t>(ks * 2),
-                      idesc, (kc | ks) != 0 ? 1u : 0u);
+            umma_tf32(tmem_base + b * 16, adesc + static_cast<uint64_t>(((ks >> 2) * kASubBytes >> 4) + (ks & 3) * 2),
+                      bdesc + static_cast<uint64_t>(((ks >> 2) * kBSubBytes >> 4) + (ks & 3) * 2), idesc,
+                      (kc | ks) != 0 ? 1u : 0u);
         }
         umma_commit(empty + 8 * s);
         if (kc == nkc - 1) umma_commit(acc_full + 8 * b);
@@ -267,15 +264,21 @@ sddmm_tc_kernel(PlanView pv, const int4* __restrict__ groups, int32_t num_groups
       mbar_wait(empty + 8 * s, ((k / kStages) & 1) ^ 1u);    // slot consumed by the MMAs of stage k - kStages
       const uint32_t a_stage = a_smem + s * kAStageBytes;
       const uint32_t b_stage = b_smem + s * kBStageBytes;
-      const int vg = kc * 8 + v;                             // vector index inside the feature row
+      const bool second = dim - kc * kChunk > 32;            // the MMAs read the second sub-block too
 #pragma unroll
       for (int u = 0; u < kPerLane; ++u) {
         const int row = u * 4 + rsub;
-        const bool valid = node[u] >= 0 && vg < nvec;
-        const float* src = x + static_cast<int64_t>(valid ? node[u] : 0) * ldx + (valid ? vg * 4 : 0);
         const uint32_t dst = (u < 32 ? a_stage + (row >> 3) * 1024 : b_stage + ((row - 128) >> 3) * 1024) +
                              sw128_offset(row & 7, v);
-        cp_async_16_hint(dst, src, valid ? 16u : 0u, policy);  // padding rows / feature tail: zero-fill
+        const uint32_t sub_step = u < 32 ? kASubBytes : kBSubBytes;
+        const float* rowp = x + static_cast<int64_t>(node[u] >= 0 ? node[u] : 0) * ldx;
+#pragma unroll
+        for (int sub = 0; sub < 2; ++sub) {
+          if (sub == 1 && !second) break;
+          const int vg = kc * (kChunk / 4) + sub * 8 + v;    // vector index inside the feature row
+          const bool valid = node[u] >= 0 && vg < nvec;
+          cp_async_16_hint(dst + sub * sub_step, rowp + (valid ? vg * 4 : 0), valid ? 16u : 0u, policy);  // zero-fill
+        }
       }
       cp_async_commit_group();
       kc += kProducers;

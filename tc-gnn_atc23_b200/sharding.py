@@ -141,7 +141,8 @@ class RowPanel:
         again: pass the result to spmm / sddmm with x_is_tf32=True.
 
         On NCCL groups with `round_tf32` the exchange is FUSED with the rounding pass (env
-        TCGNN_EXCHANGE=multicast|p2p|nccl, default: multicast when the group supports it, else p2p): the
+        TCGNN_EXCHANGE=multicast|p2p2|p2p|nccl, default: multicast when the group supports it, else the
+        two-phase balanced push p2p2): the
         gathered matrix lives in symmetric memory, and the kernel that rounds the local panel writes its
         result straight into every GPU's copy -- one multimem store through the NVSwitch, or one pass per
         peer over P2P-mapped memory -- bracketed by two device-side barriers.  No staging copy, no
@@ -194,16 +195,47 @@ class RowPanel:
             st = self._symm[d] = (buf, hdl, peers, use_mc)
         buf, hdl, peers, use_mc = st
         row_bytes = d * 4
+        w, me = self.world_size, self.rank
         hdl.barrier(channel=0)                 # every rank has finished reading the previous gathered matrix
-        if self.num_rows > 0:
-            if use_mc:
+        if use_mc:
+            if self.num_rows > 0:
                 TCGNN.round_tf32_into(x_local, int(hdl.multicast_ptr) + self.row_base * row_bytes, d, True)
-            else:
-                for k in range(self.world_size):   # step k: everybody writes to (rank + k) % world -- no hot spot
-                    p = (self.rank + k) % self.world_size
+        elif mode == "p2p" or (w <= 2 and mode != "p2p2"):
+            # direct: the rounding kernel writes the panel into every copy, one pass per peer (rotated)
+            if self.num_rows > 0:
+                for k in range(w):
+                    p = (me + k) % w
                     TCGNN.round_tf32_into(x_local, peers[p].data_ptr() + self.row_base * row_bytes, d, False)
+        else:
+            # two-phase ("p2p2", default without multicast): panels are balanced on TC blocks, so their row counts
+            # -- the bytes a rank has to send to EVERY peer -- differ 2-3x and the largest panel's owner bounds
+            # the direct exchange.  Phase A: round the panel and scatter chunk j of it into rank j's copy (1/N of
+            # the panel per peer).  Phase B: every rank now holds chunk `me` of every panel (~1/N of the matrix,
+            # whatever the panel sizes) and pushes it to all peers in one launch: equal egress on every GPU.
+            if self.num_rows > 0:
+                for k in range(w):
+                    j = (me + k) % w
+                    c0, c1 = self._chunk(me, j)
+                    if c1 > c0:
+                        TCGNN.round_tf32_into(x_local[c0 - self.row_base:c1 - self.row_base],
+                                              peers[j].data_ptr() + c0 * row_bytes, d, False)
+            hdl.barrier(channel=2)
+            begins, ends = [], []
+            for g in range(w):                 # chunk `me` of every panel, my own included
+                c0, c1 = self._chunk(g, me)
+                if c1 > c0:
+                    begins.append(c0)
+                    ends.append(c1)
+            others = [peers[(me + k) % w].data_ptr() for k in range(1, w)]
+            if begins:
+                TCGNN.push_rows(buf, others, begins, ends)
         hdl.barrier(channel=1)                 # every rank's rows have landed in every copy
         return buf
+
+    def _chunk(self, g: int, j: int):
+        """Global row range of chunk j (of world_size) of panel g."""
+        b0, rows = self.bounds[g], self.bounds[g + 1] - self.bounds[g]
+        return b0 + rows * j // self.world_size, b0 + rows * (j + 1) // self.world_size
 
     # ------------------------------------------------------------------ compute (GPU only)
     def spmm(self, x_all: torch.Tensor, edge_attention: Optional[torch.Tensor] = None,

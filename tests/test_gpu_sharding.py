@@ -94,10 +94,10 @@ def _nccl_worker(rank, world, port, q):
         x_local = torch.from_numpy(x[p.row_base:p.row_base + p.num_rows]).cuda()
         want = orc.spmm(x, rp, ci)[p.row_base:p.row_base + p.num_rows]
         ok = True
-        # the exchange three ways: NCCL uneven all-gather, fused round + P2P push, fused round + NVSwitch
-        # multicast (auto falls back to P2P when the group has no multicast support); twice each, because the
-        # second step reuses the symmetric buffer behind the barriers
-        for mode in ("nccl", "p2p", "auto"):
+        # the exchange four ways: NCCL uneven all-gather, fused round + direct P2P push, fused round + two-phase
+        # balanced push, auto (NVSwitch multicast when the group supports it); twice each, because the second
+        # step reuses the symmetric buffer behind the barriers
+        for mode in ("nccl", "p2p", "p2p2", "auto"):
             os.environ["TCGNN_EXCHANGE"] = mode
             for _ in range(2):
                 y = p.aggregate(x_local)                           # exchange + panel SpMM

@@ -18,7 +18,7 @@ rp, ci = graphgen.synthetic_graph(n, nnz, kind=kind, seed=0, device=dev)
 panel = RowPanel(rp, ci, rank, world, device=dev)
 x = graphgen.features(n, d, seed=0, device=dev)[panel.row_base:panel.row_base + panel.num_rows].contiguous()
 flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
-for mode in ("nccl", "p2p", "auto"):
+for mode in ("nccl", "p2p", "p2p2"):
     os.environ["TCGNN_EXCHANGE"] = mode
     for _ in range(3):
         panel.spmm(panel.all_gather(x, round_tf32=True), x_is_tf32=True)
@@ -35,25 +35,6 @@ for mode in ("nccl", "p2p", "auto"):
         torch.cuda.synchronize()
         tot[0] += e[0].elapsed_time(e[1]); tot[1] += e[1].elapsed_time(e[2]); tot[2] += e[0].elapsed_time(e[2])
     msg = f"[{mode}] rank {rank} rows {panel.num_rows}: exchange {tot[0]/10:.3f} ms  spmm {tot[1]/10:.3f} ms  step {tot[2]/10:.3f} ms  host-issue {host/10*1e3:.3f} ms"
-    if mode != "nccl":
-        buf, hdl, peers, use_mc = panel._symm[d]
-        msg += f"  multicast={use_mc}"
-        # phases of the fused exchange
-        ph = [0.0] * 3
-        for it in range(10):
-            flush.zero_(); torch.cuda.synchronize(); dist.barrier()
-            e = [ev() for _ in range(4)]
-            e[0].record(); hdl.barrier(channel=0); e[1].record()
-            if use_mc:
-                TCGNN.round_tf32_into(x, int(hdl.multicast_ptr) + panel.row_base * d * 4, d, True)
-            else:
-                for k in range(world):
-                    p = (rank + k) % world
-                    TCGNN.round_tf32_into(x, peers[p].data_ptr() + panel.row_base * d * 4, d, False)
-            e[2].record(); hdl.barrier(channel=1); e[3].record()
-            torch.cuda.synchronize()
-            for i in range(3): ph[i] += e[i].elapsed_time(e[i + 1])
-        msg += f"  | barrier0 {ph[0]/10:.3f}  push {ph[1]/10:.3f}  barrier1 {ph[2]/10:.3f}"
     for r in range(world):
         if r == rank: print(msg, flush=True)
         dist.barrier()
