@@ -61,3 +61,41 @@ def test_gnn_conv_surface():
     assert conv.weights.shape == (8, 4) and conv.attention_w.shape == (1, 1)
     t = gnn_conv.gen_test_tensor(torch.zeros(5, 3))
     assert t.tolist() == [[float(i)] * 3 for i in range(5)]
+
+
+REFERENCE = "/root/reference"
+
+
+@pytest.mark.skipif(not __import__("os").path.isdir(REFERENCE), reason="reference checkout not present (GPU box)")
+def test_reference_python_layer_binds_to_our_module():
+    """Drop-in boundary, checked against the reference's OWN Python sources (build container only): every
+    `TCGNN.<name>` that gnn_conv.py / main_tcgnn.py use exists in our extension module, and the reference's
+    gnn_conv.py imports and builds its layers on top of it unchanged."""
+    import importlib.util
+    import os
+    import re
+    import sys
+    import TCGNN
+    used = set()
+    for f in ("gnn_conv.py", "main_tcgnn.py"):
+        used |= set(re.findall(r"\bTCGNN\.(\w+)\s*\(", open(os.path.join(REFERENCE, f)).read()))
+    assert used >= {"forward", "forward_ef", "forward_AGNN", "preprocess"}
+    missing = [n for n in sorted(used) if not hasattr(TCGNN, n)]
+    assert not missing, f"reference calls TCGNN.{missing} which our module does not export"
+    for n in ("preprocess_gpu", "backward", "backward_ef", "SDDMM_forward"):      # TCGNN.cpp:260-272 + north star alias
+        assert hasattr(TCGNN, n)
+    spec = importlib.util.spec_from_file_location("reference_gnn_conv", os.path.join(REFERENCE, "gnn_conv.py"))
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules.setdefault("TCGNN", TCGNN)
+    spec.loader.exec_module(mod)                       # `import TCGNN` inside resolves to ours
+    assert mod.TCGNN is TCGNN
+    for cls in ("GCNConv", "GINConv", "AGNNConv", "SAG"):
+        assert hasattr(mod, cls)
+    conv = mod.GCNConv(8, 4)
+    assert tuple(conv.weights.shape) == (8, 4)
+    # same positional call contract as ours: CPU tensors must be rejected by the op with a RuntimeError
+    # (CHECK_INPUT in the reference, TCGNN.cpp:54-56), not crash
+    x = torch.zeros(4, 8)
+    i = torch.zeros(5, dtype=torch.int32)
+    with pytest.raises(RuntimeError):
+        TCGNN.forward(x, i, i, i, i, i)
