@@ -20,6 +20,7 @@ calls go to the `TCGNN` extension and need a GPU -- there is no CPU fallback.
 from __future__ import annotations
 
 import os
+import sys
 from typing import List, Optional, Sequence
 
 import torch
@@ -124,6 +125,7 @@ class RowPanel:
                                        BLK_W, self.blockPartition, self.edgeToColumn, self.edgeToRow)
         self._x_all = None
         self._symm = {}    # feature width -> (symmetric buffer, handle, peer views, multicast?)
+        self._symm_unavailable = False
 
     # ------------------------------------------------------------------ exchange
     @property
@@ -153,8 +155,17 @@ class RowPanel:
         d = x_local.shape[1]
         mode = os.environ.get("TCGNN_EXCHANGE", "auto")
         if (round_tf32 and out is None and self.world_size > 1 and x_local.is_cuda and d % 4 == 0
-                and mode != "nccl" and dist.get_backend(group) == "nccl"):
-            return self._fused_exchange(x_local.contiguous(), group, mode)
+                and mode != "nccl" and not self._symm_unavailable and dist.get_backend(group) == "nccl"):
+            try:
+                return self._fused_exchange(x_local.contiguous(), group, mode)
+            except (RuntimeError, ImportError, AttributeError) as exc:
+                # symmetric memory needs P2P access + a working rendezvous on every rank; the failure is collective
+                # (same platform everywhere), so every rank falls back to the NCCL all-gather together
+                if mode != "auto":
+                    raise
+                self._symm_unavailable = True
+                print(f"[tcgnn sharding] rank {self.rank}: fused exchange unavailable ({exc}); using NCCL all-gather",
+                      file=sys.stderr, flush=True)
         if round_tf32 and self.num_rows > 0:
             import TCGNN
             x_local = TCGNN.round_tf32(x_local.contiguous())

@@ -127,3 +127,19 @@ def test_module_rejects_cpu_tensors_for_compute(capi):
         TCGNN.forward(x, i, e, b, e, e)
     with pytest.raises(RuntimeError, match="must be a CUDA tensor"):
         TCGNN.forward_ef(x, i, e, b, e, e)
+
+
+def test_optional_entry_points_validate_arguments_without_a_gpu(capi):
+    """Argument checks of the round / push / *_ex entry points run before any CUDA call."""
+    import ctypes as C
+    L = capi.lib()
+    assert L.tcgnn_round_tf32(None, 4, None, 4, 1, 4, None) == -1
+    assert L.tcgnn_round_tf32_multicast(None, 4, None, 4, 1, 4, None) == -1
+    assert b"tcgnn_round_tf32" in L.tcgnn_last_error()
+    buf = (C.c_float * 64)()
+    addr = C.addressof(buf)
+    assert L.tcgnn_round_tf32(addr, 4, addr + 4, 4, 1, 4, None) == -1          # out not 16-byte aligned
+    assert L.tcgnn_round_tf32(addr, 4, addr, 6, 1, 4, None) == -1              # ldo % 4 != 0
+    assert L.tcgnn_push_rows(None, None, 0, None, None, 0, 4, None) == -1
+    assert L.tcgnn_spmm_f32_ex(None, None, 0, None, None, 0, 0, 0, None) == -1
+    assert L.tcgnn_sddmm_f32_ex(None, None, 0, None, 0, 0, None) == -1
