@@ -135,6 +135,15 @@ int tcgnn_spmm_f32_ex(tcgnn_plan* plan, const float* x, int64_t ldx, const float
 int tcgnn_sddmm_f32_ex(tcgnn_plan* plan, const float* x, int64_t ldx, float* edge_out, int32_t dim,
                        uint32_t flags, void* stream);
 
+/* SpMM with HOST feature / result buffers (the end-to-end path of a caller whose features live in host memory;
+ * page-locked buffers for full PCIe speed).  x_host: [num_cols, ldx], y_host: [num_nodes, ldy] in host memory;
+ * edge_weight stays a DEVICE pointer (CSR edge order) or NULL.  The H2D copy of X and the D2H copy of Y run on
+ * plan-owned copy streams around the kernels.  Ordered
+ * on `stream` like every other call: it waits for work queued before it, and `stream` waits for the last copy,
+ * so synchronising `stream` (or an event recorded on it) makes y_host valid.  Device staging is plan-owned. */
+int tcgnn_spmm_f32_host(tcgnn_plan* plan, const float* x_host, int64_t ldx, const float* edge_weight, float* y_host,
+                        int64_t ldy, int32_t dim, void* stream);
+
 /* Bring-up / layout diagnostics (used by tests/test_gpu_umma_layouts.py): copies the two byte images
  * into 1024-byte aligned shared memory, issues `ksteps` tcgen05.mma.kind::tf32 (M=128) whose
  * descriptors are adesc/bdesc (start-address field 0) plus the image base plus k*a_step_bytes /

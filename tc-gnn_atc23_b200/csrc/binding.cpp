@@ -10,6 +10,7 @@
 //   * `preprocess_gpu` is a real implementation (the reference's is a stub that prints 0).
 // The kernel-side plan is derived once per graph and cached, keyed on the storages of the five
 // SGT tensors (weak references + version counters, so a freed or mutated graph never hits).
+#include <c10/cuda/CUDAException.h>
 #include <c10/cuda/CUDAGuard.h>
 #include <c10/cuda/CUDAStream.h>
 #include <torch/extension.h>
@@ -381,6 +382,43 @@ void round_tf32_into(torch::Tensor input, int64_t out_ptr, int64_t ldo, bool mul
   check_status(st, "tcgnn_round_tf32");
 }
 
+// SpMM with host feature / result tensors (tcgnn_spmm_f32_host): X and Y are CPU tensors (pinned for full speed),
+// the graph tensors are CUDA tensors.  Returns y_host; with sync = false the caller must synchronise the current
+// stream (or an event recorded on it) before reading it.
+torch::Tensor forward_host(torch::Tensor x_host, torch::Tensor nodePointer, torch::Tensor edgeList,
+                           torch::Tensor blockPartition, torch::Tensor edgeToColumn, torch::Tensor edgeToRow,
+                           c10::optional<torch::Tensor> y_host_opt, bool sync) {
+  TORCH_CHECK(!x_host.is_cuda() && x_host.is_contiguous() && x_host.scalar_type() == torch::kFloat32 &&
+                  x_host.dim() == 2,
+              "x_host must be a contiguous float32 CPU tensor [num_nodes, dim]");
+  CHECK_INPUT(nodePointer);
+  CHECK_INPUT(edgeList);
+  CHECK_INPUT(blockPartition);
+  CHECK_INPUT(edgeToColumn);
+  CHECK_INPUT(edgeToRow);
+  CHECK_I32(nodePointer);
+  CHECK_I32(edgeList);
+  CHECK_I32(blockPartition);
+  CHECK_I32(edgeToColumn);
+  CHECK_I32(edgeToRow);
+  const int64_t n = nodePointer.size(0) - 1;
+  TORCH_CHECK(x_host.size(0) == n, "x_host has ", x_host.size(0), " rows but the graph has ", n, " nodes");
+  torch::Tensor y_host = y_host_opt.has_value()
+                             ? *y_host_opt
+                             : torch::empty({n, x_host.size(1)}, x_host.options().pinned_memory(true));
+  TORCH_CHECK(!y_host.is_cuda() && y_host.is_contiguous() && y_host.scalar_type() == torch::kFloat32 &&
+                  y_host.dim() == 2 && y_host.size(0) == n && y_host.size(1) == x_host.size(1),
+              "y_host must be a contiguous float32 CPU tensor [num_nodes, dim]");
+  c10::cuda::CUDAGuard guard(nodePointer.device());
+  tcgnn_plan* plan = get_plan(nodePointer, edgeList, blockPartition, edgeToColumn, edgeToRow);
+  auto stream = c10::cuda::getCurrentCUDAStream(nodePointer.get_device()).stream();
+  check_status(tcgnn_spmm_f32_host(plan, x_host.data_ptr<float>(), x_host.size(1), nullptr, y_host.data_ptr<float>(),
+                                   y_host.size(1), static_cast<int32_t>(x_host.size(1)), stream),
+               "tcgnn_spmm_f32_host");
+  if (sync) C10_CUDA_CHECK(cudaStreamSynchronize(stream));
+  return y_host;
+}
+
 // Second phase of the balanced exchange: rows [begin, end) segments of `local` -> the same rows at every peer address.
 void push_rows(torch::Tensor local, std::vector<int64_t> peer_ptrs, std::vector<int64_t> seg_begin,
                std::vector<int64_t> seg_end) {
@@ -428,6 +466,10 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("round_tf32_into", &round_tf32_into,
         "(input, out_ptr, ldo, multicast): cvt.rna.tf32(input) written to a raw (local / peer / multicast) address",
         py::arg("input"), py::arg("out_ptr"), py::arg("ldo"), py::arg("multicast") = false);
+  m.def("forward_host", &forward_host,
+        "SpMM with host (pinned) feature / result tensors: pipelined H2D copy, kernels, D2H copy",
+        py::arg("x_host"), py::arg("nodePointer"), py::arg("edgeList"), py::arg("blockPartition"),
+        py::arg("edgeToColumn"), py::arg("edgeToRow"), py::arg("y_host") = py::none(), py::arg("sync") = true);
   m.def("push_rows", &push_rows, "(local, peer_ptrs, seg_begin_rows, seg_end_rows): copy row segments to peers");
   m.def("round_tf32", &round_tf32, "cvt.rna.tf32 of a [rows, dim] CUDA matrix (dim % 4 == 0), for x_is_tf32 = True");
   m.def("clear_plan_cache", &clear_plan_cache, "Destroy all cached kernel plans");

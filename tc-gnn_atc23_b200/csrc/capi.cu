@@ -156,6 +156,17 @@ int tcgnn_spmm_f32(tcgnn_plan* plan, const float* x, int64_t ldx, const float* e
   return tcgnn_spmm_f32_ex(plan, x, ldx, edge_weight, y, ldy, dim, 0u, stream);
 }
 
+int tcgnn_spmm_f32_host(tcgnn_plan* plan, const float* x_host, int64_t ldx, const float* edge_weight, float* y_host,
+                        int64_t ldy, int32_t dim, void* stream) {
+  int st = check_op("tcgnn_spmm_f32_host", plan, x_host, ldx, y_host, dim);
+  if (st != TCGNN_OK) return st;
+  if (ldy < dim) {
+    set_last_error("tcgnn_spmm_f32_host: ldy < dim");
+    return TCGNN_ERR_INVALID_ARG;
+  }
+  return spmm_host_launch(plan, x_host, ldx, edge_weight, y_host, ldy, dim, static_cast<cudaStream_t>(stream));
+}
+
 int tcgnn_sddmm_f32_ex(tcgnn_plan* plan, const float* x, int64_t ldx, float* edge_out, int32_t dim, uint32_t flags,
                        void* stream) {
   if (plan != nullptr && plan->num_edges == 0) return TCGNN_OK;

@@ -424,6 +424,93 @@ int plan_ensure_scratch(tcgnn_plan* p, float** slot, size_t count) {
   return TCGNN_OK;
 }
 
+// SpMM with HOST feature / result buffers (pinned memory for full speed): host -> device copy of X, the kernels
+// and the device -> host copy of Y on the plan's copy streams and the caller's stream.  Ordered on `stream`: work queued before the call is waited for, and `stream`
+// waits for the last copy, so a later cudaStreamSynchronize(stream) / event covers y_host.
+int spmm_host_launch(tcgnn_plan* p, const float* x_host, int64_t ldx, const float* edge_weight, float* y_host,
+                     int64_t ldy, int32_t dim, cudaStream_t stream) {
+  const size_t need_x = static_cast<size_t>(p->num_cols) * dim, need_y = static_cast<size_t>(p->num_nodes) * dim;
+  {
+    std::lock_guard<std::mutex> lock(p->mu);
+    cudaError_t e = cudaSuccess;
+    if (p->h2d_stream == nullptr) {
+      e = cudaStreamCreateWithFlags(&p->h2d_stream, cudaStreamNonBlocking);
+      if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p->d2h_stream, cudaStreamNonBlocking);
+      for (int i = 0; e == cudaSuccess && i < 6; ++i) e = cudaEventCreateWithFlags(&p->host_ev[i], cudaEventDisableTiming);
+    }
+    if (e == cudaSuccess && (p->host_x_cap < need_x || p->host_y_cap < need_y)) {
+      e = cudaStreamSynchronize(stream);   // the old staging buffers may still be in use
+      if (e == cudaSuccess && p->host_x_cap < need_x) {
+        if (p->host_x_dev) cudaFree(p->host_x_dev);
+        p->host_x_dev = nullptr;
+        p->host_x_cap = 0;
+        e = cudaMalloc(&p->host_x_dev, need_x * sizeof(float));
+        if (e == cudaSuccess) p->host_x_cap = need_x;
+      }
+      if (e == cudaSuccess && p->host_y_cap < need_y) {
+        if (p->host_y_dev) cudaFree(p->host_y_dev);
+        p->host_y_dev = nullptr;
+        p->host_y_cap = 0;
+        e = cudaMalloc(&p->host_y_dev, need_y * sizeof(float));
+        if (e == cudaSuccess) p->host_y_cap = need_y;
+      }
+    }
+    if (e != cudaSuccess) {
+      set_last_error("tcgnn_spmm_f32_host: staging setup failed: %s", cudaGetErrorString(e));
+      return e == cudaErrorMemoryAllocation ? TCGNN_ERR_OOM : TCGNN_ERR_CUDA;
+    }
+  }
+  // One chunk.  Pipelining over two feature-column chunks (SpMM is independent per column) was measured and
+  // rejected: the column halves are strided on the host side, and 256-byte-row cudaMemcpy2DAsync transfers ran at
+  // ~15 GB/s instead of ~57 GB/s (e2e 18.0 ms vs 7.4 ms on the reddit-sized graph, profiles/r01j_*).
+  const int nchunk = 1;
+  const int32_t wc = dim / nchunk;
+  cudaEvent_t* ev = p->host_ev;
+  int status = TCGNN_OK;
+#define HOST_CUDA(expr)                                                                    \
+  do {                                                                                     \
+    cudaError_t _e = (expr);                                                               \
+    if (_e != cudaSuccess) {                                                               \
+      set_last_error("tcgnn_spmm_f32_host: %s failed: %s", #expr, cudaGetErrorString(_e)); \
+      return TCGNN_ERR_CUDA;                                                               \
+    }                                                                                      \
+  } while (0)
+  HOST_CUDA(cudaEventRecord(ev[0], stream));
+  HOST_CUDA(cudaStreamWaitEvent(p->h2d_stream, ev[0], 0));
+  HOST_CUDA(cudaStreamWaitEvent(p->d2h_stream, ev[0], 0));
+  for (int c = 0; c < nchunk; ++c) {
+    float* xd = p->host_x_dev + static_cast<size_t>(p->num_cols) * wc * c;
+    if (ldx == wc) {
+      HOST_CUDA(cudaMemcpyAsync(xd, x_host, sizeof(float) * need_x, cudaMemcpyHostToDevice, p->h2d_stream));
+    } else {
+      HOST_CUDA(cudaMemcpy2DAsync(xd, sizeof(float) * wc, x_host + static_cast<size_t>(wc) * c, sizeof(float) * ldx,
+                                  sizeof(float) * wc, static_cast<size_t>(p->num_cols), cudaMemcpyHostToDevice,
+                                  p->h2d_stream));
+    }
+    HOST_CUDA(cudaEventRecord(ev[1 + c], p->h2d_stream));
+  }
+  for (int c = 0; c < nchunk; ++c) {
+    const float* xd = p->host_x_dev + static_cast<size_t>(p->num_cols) * wc * c;
+    float* yd = p->host_y_dev + static_cast<size_t>(p->num_nodes) * wc * c;
+    HOST_CUDA(cudaStreamWaitEvent(stream, ev[1 + c], 0));
+    status = spmm_launch(p, xd, wc, edge_weight, yd, wc, wc, 0u, stream);
+    if (status != TCGNN_OK) return status;
+    HOST_CUDA(cudaEventRecord(ev[3 + c], stream));
+    HOST_CUDA(cudaStreamWaitEvent(p->d2h_stream, ev[3 + c], 0));
+    if (ldy == wc) {
+      HOST_CUDA(cudaMemcpyAsync(y_host, yd, sizeof(float) * need_y, cudaMemcpyDeviceToHost, p->d2h_stream));
+    } else {
+      HOST_CUDA(cudaMemcpy2DAsync(y_host + static_cast<size_t>(wc) * c, sizeof(float) * ldy, yd, sizeof(float) * wc,
+                                  sizeof(float) * wc, static_cast<size_t>(p->num_nodes), cudaMemcpyDeviceToHost,
+                                  p->d2h_stream));
+    }
+  }
+  HOST_CUDA(cudaEventRecord(ev[5], p->d2h_stream));
+  HOST_CUDA(cudaStreamWaitEvent(stream, ev[5], 0));
+#undef HOST_CUDA
+  return TCGNN_OK;
+}
+
 int plan_destroy(tcgnn_plan* p) {
   if (p == nullptr) return TCGNN_OK;
   if (p->tiles) cudaFree(p->tiles);
@@ -435,6 +522,12 @@ int plan_destroy(tcgnn_plan* p) {
   if (p->x_round) cudaFree(p->x_round);
   if (p->groups) cudaFree(p->groups);
   if (p->flag) cudaFree(p->flag);
+  if (p->host_x_dev) cudaFree(p->host_x_dev);
+  if (p->host_y_dev) cudaFree(p->host_y_dev);
+  if (p->h2d_stream) cudaStreamDestroy(p->h2d_stream);
+  if (p->d2h_stream) cudaStreamDestroy(p->d2h_stream);
+  for (cudaEvent_t ev : p->host_ev)
+    if (ev) cudaEventDestroy(ev);
   delete p;
   return TCGNN_OK;
 }

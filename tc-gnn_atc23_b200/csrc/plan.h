@@ -34,6 +34,12 @@ struct tcgnn_plan {
   int4* groups = nullptr;             // [num_groups]  lazy: SDDMM work units {tile_start, ntiles, win, 0}
   int32_t num_groups = 0;
   int32_t* flag = nullptr;            // device error counter
+  // host-buffer entry point (tcgnn_spmm_f32_host): device staging + copy streams, lazy
+  float* host_x_dev = nullptr;        // [num_cols * dim] column chunks, packed
+  float* host_y_dev = nullptr;        // [num_nodes * dim]
+  size_t host_x_cap = 0, host_y_cap = 0;
+  cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
+  cudaEvent_t host_ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // start, h2d[2], kernel[2], done
   std::mutex mu;                      // guards the lazy members
 
   tcgnn::PlanView view() const {
@@ -77,6 +83,8 @@ int sddmm_launch(tcgnn_plan* plan, const float* x, int64_t ldx, float* edge_out,
                  cudaStream_t stream);
 int push_rows_launch(const float* src, float* const* peers, int32_t n_peers, const int64_t* seg_begin_rows,
                      const int64_t* seg_end_rows, int32_t n_segs, int64_t ld, cudaStream_t stream);
+int spmm_host_launch(tcgnn_plan* plan, const float* x_host, int64_t ldx, const float* edge_weight, float* y_host,
+                     int64_t ldy, int32_t dim, cudaStream_t stream);
 int round_tf32_launch(const float* x, int64_t ldx, float* out, int64_t ldo, int64_t rows, int32_t dim, int multimem,
                       cudaStream_t stream);
 int sgt_cuda(const int32_t* row_ptr, const int32_t* col_idx, int32_t num_nodes, int32_t num_cols, int64_t num_edges,

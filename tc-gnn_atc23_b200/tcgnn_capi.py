@@ -49,6 +49,8 @@ def lib() -> C.CDLL:
         L.tcgnn_spmm_f32_ex.argtypes = [vp, vp, i64, vp, vp, i64, i32, u32, vp]
         L.tcgnn_sddmm_f32_ex.argtypes = [vp, vp, i64, vp, i32, u32, vp]
         L.tcgnn_round_tf32.argtypes = [vp, i64, vp, i64, i64, i32, vp]
+        L.tcgnn_spmm_f32_host.argtypes = [vp, vp, i64, vp, vp, i64, i32, vp]
+        L.tcgnn_spmm_f32_host.restype = C.c_int
         L.tcgnn_push_rows.argtypes = [vp, vp, i32, vp, vp, i32, i64, vp]
         L.tcgnn_push_rows.restype = C.c_int
         L.tcgnn_round_tf32_multicast.argtypes = [vp, i64, vp, i64, i64, i32, vp]
