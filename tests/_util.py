@@ -62,3 +62,16 @@ def assert_normwise(got, want, scale, tol, what=""):
         raise AssertionError(
             f"{what}: {int(bad.sum())} of {bad.size} elements outside {tol:g}*sum|terms|; first at {tuple(idx)}: "
             f"got {got[tuple(idx)]!r} want {want[tuple(idx)]!r} scale {np.asarray(scale)[tuple(idx)]!r}")
+
+
+def assert_equal_up_to_split_windows(a, b, what="", max_rows=2 * 148 * 16, rtol=1e-5):
+    """Two SpMM runs are bit-identical except in the rows of windows that are cut by a CTA slice boundary: their
+    partial sums are combined with fp32 atomics / bulk reduce-adds, whose order is timing dependent when a hub
+    window spans three or more CTAs.  Those rows (at most two windows per CTA) must still agree to rounding."""
+    import torch
+    diff = (a != b).any(dim=1)
+    n_diff = int(diff.sum())
+    assert n_diff <= max_rows, f"{what}: {n_diff} rows differ between two runs (more than the split windows can explain)"
+    if n_diff:
+        scale = torch.maximum(a[diff].abs().amax(dim=1, keepdim=True), b[diff].abs().amax(dim=1, keepdim=True))
+        assert bool(((a[diff] - b[diff]).abs() <= rtol * scale + 1e-30).all()), f"{what}: split-window rows differ beyond rounding"

@@ -95,7 +95,8 @@ def test_spmm_full_size_linearity(reddit):
     x = torch.randn(N, D, generator=torch.Generator(device="cuda").manual_seed(6), device="cuda")
     y1 = TCGNN.forward(x, rp, ci, bp, e2c, e2r)[0]
     y2 = TCGNN.forward(x * 2, rp, ci, bp, e2c, e2r)[0]
-    assert torch.equal(y1 * 2, y2)
+    from _util import assert_equal_up_to_split_windows
+    assert_equal_up_to_split_windows(y1 * 2, y2, "SpMM(2X) vs 2 SpMM(X)")
     y3 = TCGNN.forward(x, rp, ci, bp, e2c, e2r)[0]
     # windows split over CTAs are combined with fp32 atomics: only those rows may differ between runs
     same = (y1 == y3).all(dim=1)
