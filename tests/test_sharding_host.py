@@ -133,3 +133,31 @@ def test_partition_on_tc_blocks_balances_tiles():
         tiles_nnz = [int(bp[nnz_b[i] // 16:(nnz_b[i + 1] + 15) // 16].sum()) for i in range(world)]
         tiles_tc = [int(bp[b[i] // 16:(b[i + 1] + 15) // 16].sum()) for i in range(world)]
         assert max(tiles_tc) <= max(tiles_nnz)
+
+
+@pytest.mark.parametrize("world", [2, 3, 4, 8])
+def test_two_phase_exchange_chunks_tile_every_panel(world):
+    """The balanced exchange scatters chunk j of panel g to rank j and lets rank j forward it: the chunks of a panel
+    must tile it exactly, and the chunks held by one rank after phase A (one per panel) must be disjoint."""
+    from sharding import RowPanel
+    n = 10007
+    rp, ci = orc.rmat_graph(n, 200000, seed=40 + world)
+    t_rp, t_ci = torch.from_numpy(rp), torch.from_numpy(ci)
+    bp, e2c, e2r, _ = orc.sgt(rp, ci, n)
+    sgt = tuple(torch.from_numpy(a) for a in (bp, e2c, e2r))
+    p = RowPanel(t_rp, t_ci, 0, world, sgt=sgt)          # TC-block-balanced bounds, sliced SGT
+    covered = np.zeros(n, dtype=np.int32)
+    for g in range(world):
+        prev = p.bounds[g]
+        for j in range(world):
+            c0, c1 = p._chunk(g, j)
+            assert c0 == prev and c1 >= c0
+            covered[c0:c1] += 1
+            prev = c1
+        assert prev == p.bounds[g + 1]
+    assert (covered == 1).all()
+    for j in range(world):                               # what rank j holds after phase A
+        held = [p._chunk(g, j) for g in range(world)]
+        assert all(a[1] <= b[0] for a, b in zip(held, held[1:]))
+        rows = sum(c1 - c0 for c0, c1 in held)
+        assert abs(rows - n / world) <= world            # ~1/N of the matrix whatever the panel sizes
