@@ -15,6 +15,10 @@
  *   tcgnn_spmm_f32     <- spmm_forward_cuda     TCGNN_conv/TCGNN_kernel.cu:175-220 (kernel :336-454)
  *                         spmmAGNN_forward_cuda TCGNN_conv/TCGNN_kernel.cu:227-279 (kernel :459-578)
  *   tcgnn_sddmm_f32    <- sddmm_forward_cuda    TCGNN_conv/TCGNN_kernel.cu:286-327 (kernel :584-728)
+ *   tcgnn_agnn_f32     <- the AGNN edge pipeline of gnn_conv.py:125-132 (forward_ef -> torch.mm with attention_w ->
+ *                         transpose/contiguous -> forward_AGNN) as one call
+ *   tcgnn_csr_transpose<- (new) A^T for a backward pass that is correct on directed graphs; the reference re-uses
+ *                         the forward CSR, i.e. assumes A == A^T (gnn_conv.py:76-85)
  *   tcgnn_plan_*       <- (new) the kernel-side layout derived once per graph from the SGT arrays;
  *                         the reference re-derives it inside every kernel launch by rescanning all
  *                         window edges per tile (TCGNN_kernel.cu:399-408).
@@ -86,7 +90,9 @@ int tcgnn_plan_create(const int32_t* row_ptr, const int32_t* col_idx, const int3
  * (edge_to_row rebased to the panel), col_idx keeps GLOBAL node ids in [0, num_cols).  X passed to
  * the kernels has num_cols rows; SpMM writes the panel's num_rows output rows; SDDMM reads the
  * panel's own feature rows at X[row_base + r].  tcgnn_plan_create == panel with num_cols ==
- * num_rows and row_base == 0. */
+ * num_rows and row_base == 0.  row_base == -1: the plan's rows are not rows of X at all (a partial
+ * product over one source panel's packed rows: col_idx indexes that block, num_cols may be smaller than
+ * num_rows); such a plan serves SpMM only. */
 int tcgnn_plan_create_panel(const int32_t* row_ptr, const int32_t* col_idx, const int32_t* block_partition,
                             const int32_t* edge_to_col, const int32_t* edge_to_row, int32_t num_rows,
                             int32_t num_cols, int32_t row_base, int64_t num_edges, int32_t num_windows,
@@ -118,6 +124,12 @@ int tcgnn_sddmm_f32(tcgnn_plan* plan, const float* x, int64_t ldx, float* edge_o
  * (otherwise the op packs a copy as usual).  out: [rows, ldo] with ldo % 4 == 0, 16-byte aligned; columns
  * [dim, ldo) are zero-filled. */
 #define TCGNN_X_IS_TF32 1u
+/* SpMM only: Y += A X instead of Y = A X (nothing is cleared; every window is combined with fp32 reduce-adds).  Used
+ * by the sharded path, which adds one partial product per source panel as that panel's rows arrive. */
+#define TCGNN_ACCUMULATE 2u
+/* SpMM only: `edge_weight` is not in CSR edge order but already the plan's tile-ordered, tf32-rounded weight stream
+ * ([pairs] floats, pairs = tcgnn_plan_info()[5]) -- what tcgnn_agnn_f32 leaves in `att_tile_out`. */
+#define TCGNN_W_TILE_ORDER 4u
 int tcgnn_round_tf32(const float* x, int64_t ldx, float* out, int64_t ldo, int64_t rows, int32_t dim, void* stream);
 /* Same, fused with the exchange of row-panel sharding: `out` may be PEER memory (a P2P-mapped pointer into another
  * GPU's gathered matrix) -- the rounded rows are written straight over NVLink -- and tcgnn_round_tf32_multicast
@@ -135,6 +147,35 @@ int tcgnn_spmm_f32_ex(tcgnn_plan* plan, const float* x, int64_t ldx, const float
 int tcgnn_sddmm_f32_ex(tcgnn_plan* plan, const float* x, int64_t ldx, float* edge_out, int32_t dim,
                        uint32_t flags, void* stream);
 
+/* Fused AGNN edge pipeline (reference gnn_conv.py:125-132):
+ *     score[e] = <tf32(X[row(e)]), tf32(X[col(e)])>           (SDDMM, TCGNN_kernel.cu:584-728)
+ *     att[e]   = score[e] * attention_w[0]                     (torch.mm with the [1, n_heads = 1] parameter)
+ *     Y        = (A o tf32(att)) tf32(X)                        (weighted SpMM, TCGNN_kernel.cu:459-578)
+ * in one call: X is rounded once, the SDDMM epilogue writes tf32(att) in the plan's tile order, and the weighted SpMM
+ * consumes that stream directly -- no CSR-order [E] round trip, no permutation passes.  attention_w: DEVICE pointer
+ * to one float (the layer's parameter; NULL = 1.0).  att_tile_out (nullable): [pairs] floats that receive tf32(att)
+ * in tile order, for a backward pass via tcgnn_spmm_f32_ex(..., TCGNN_W_TILE_ORDER); NULL uses plan scratch.
+ * edge_out (nullable): [num_edges] raw scores in CSR edge order (== tcgnn_sddmm_f32).  Results are bit-identical to
+ * the three separate calls. */
+int tcgnn_agnn_f32(tcgnn_plan* plan, const float* x, int64_t ldx, const float* attention_w, float* y, int64_t ldy,
+                   float* att_tile_out, float* edge_out, int32_t dim, uint32_t flags, void* stream);
+
+/* A^T of a device CSR (unsorted rows allowed): row_ptr_t [num_cols + 1], col_idx_t [num_edges] and, when non-null,
+ * edge_map_t [num_edges] = CSR edge id in A of every edge of A^T (to carry edge weights over).  The order of the
+ * entries inside a row of A^T is unspecified (SGT, the plan and every kernel here accept unsorted rows; results
+ * depend only on the set of (row, col) pairs).  num_rows x num_cols is A's shape.  Synchronises `stream`. */
+int tcgnn_csr_transpose(const int32_t* row_ptr, const int32_t* col_idx, int32_t num_rows, int32_t num_cols,
+                        int64_t num_edges, int32_t* row_ptr_t, int32_t* col_idx_t, int32_t* edge_map_t, void* stream);
+
+/* dst[i, :] = src[rows[i], :] for i < n_rows (rows of `ld` floats, ld % 4 == 0, 16-byte aligned): packs the feature
+ * rows another GPU's panel references into a contiguous block for the exchange (sharding.py). */
+int tcgnn_gather_rows(const float* src, int64_t ld, const int32_t* rows, int64_t n_rows, float* dst, void* stream);
+
+/* Stream-ordered flag wait for the overlapped exchange: blocks `stream` (one spinning thread, ld.acquire.sys) until
+ * (int32)(*flag - value) >= 0.  `flag` is device memory a peer GPU's copy engine writes after its rows have landed.
+ * timeout_ms > 0: gives up after that long and sets *error_out (device int32, nullable) to 1 instead of hanging. */
+int tcgnn_stream_wait_flag(const int32_t* flag, int32_t value, int32_t timeout_ms, int32_t* error_out, void* stream);
+
 /* SpMM with HOST feature / result buffers (the end-to-end path of a caller whose features live in host memory;
  * page-locked buffers for full PCIe speed).  x_host: [num_cols, ldx], y_host: [num_nodes, ldy] in host memory;
  * edge_weight stays a DEVICE pointer (CSR edge order) or NULL.  The H2D copy of X and the D2H copy of Y run on
@@ -143,6 +184,14 @@ int tcgnn_sddmm_f32_ex(tcgnn_plan* plan, const float* x, int64_t ldx, float* edg
  * so synchronising `stream` (or an event recorded on it) makes y_host valid.  Device staging is plan-owned. */
 int tcgnn_spmm_f32_host(tcgnn_plan* plan, const float* x_host, int64_t ldx, const float* edge_weight, float* y_host,
                         int64_t ldy, int32_t dim, void* stream);
+
+/* SDDMM / fused AGNN with HOST buffers, same conventions as tcgnn_spmm_f32_host: x_host [num_cols, ldx] in, results
+ * out to host memory (edge_out_host [num_edges]; y_host [num_nodes, ldy]; either AGNN output may be NULL except
+ * y_host).  attention_w stays a DEVICE pointer. */
+int tcgnn_sddmm_f32_host(tcgnn_plan* plan, const float* x_host, int64_t ldx, float* edge_out_host, int32_t dim,
+                         void* stream);
+int tcgnn_agnn_f32_host(tcgnn_plan* plan, const float* x_host, int64_t ldx, const float* attention_w, float* y_host,
+                        int64_t ldy, float* edge_out_host, int32_t dim, void* stream);
 
 /* Bring-up / layout diagnostics (used by tests/test_gpu_umma_layouts.py): copies the two byte images
  * into 1024-byte aligned shared memory, issues `ksteps` tcgen05.mma.kind::tf32 (M=128) whose

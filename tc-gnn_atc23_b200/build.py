@@ -28,9 +28,10 @@ CUDA_HOME = os.environ.get("CUDA_HOME", "/usr/local/cuda")
 NVCC = os.path.join(CUDA_HOME, "bin", "nvcc")
 
 LIB_NAME = "libtcgnn_b200.so"
-CU_SOURCES = ["capi.cu", "plan.cu", "round_pack.cu", "spmm_tc.cu", "sddmm_tc.cu", "sgt_gpu.cu", "umma_probe.cu"]
+CU_SOURCES = ["capi.cu", "plan.cu", "round_pack.cu", "spmm_tc.cu", "sddmm_tc.cu", "sgt_gpu.cu", "graph_ops.cu",
+              "host_entry.cu", "umma_probe.cu"]
 CPP_SOURCES = ["sgt_cpu.cpp"]
-HEADERS = ["common.cuh", "plan.h", os.path.join(INCLUDE, "tcgnn_b200.h")]
+HEADERS = ["common.cuh", "plan.h", "scan.cuh", os.path.join(INCLUDE, "tcgnn_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

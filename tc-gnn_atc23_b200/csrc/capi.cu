@@ -87,8 +87,8 @@ int tcgnn_plan_create_panel(const int32_t* row_ptr, const int32_t* col_idx, cons
   *plan_out = nullptr;
   const int64_t expect_windows = (static_cast<int64_t>(num_rows) + TCGNN_BLK_H - 1) / TCGNN_BLK_H;
   if (row_ptr == nullptr || block_partition == nullptr || num_rows <= 0 || num_edges < 0 ||
-      num_edges > 0x7FFFFFFFLL || num_windows != expect_windows || row_base < 0 ||
-      static_cast<int64_t>(row_base) + num_rows > num_cols ||
+      num_edges > 0x7FFFFFFFLL || num_windows != expect_windows || row_base < -1 || num_cols < 1 ||
+      (row_base >= 0 && static_cast<int64_t>(row_base) + num_rows > num_cols) ||
       (num_edges > 0 && (col_idx == nullptr || edge_to_col == nullptr || edge_to_row == nullptr))) {
     set_last_error("tcgnn_plan_create: bad argument (num_rows=%d num_cols=%d row_base=%d num_edges=%lld "
                    "num_windows=%d, expected %lld windows of %d rows)",
@@ -117,7 +117,7 @@ int tcgnn_plan_info(const tcgnn_plan* plan, int64_t info[8]) {
   info[3] = plan->num_tiles;
   info[4] = static_cast<int64_t>(sizeof(TileMeta)) * (plan->num_tiles + 1) +
             4 * (static_cast<int64_t>(plan->num_windows) + 1) + (plan->eperm ? 4LL * plan->num_pairs : 0) +
-            (plan->weight_perm ? 4LL * plan->num_pairs : 0) + (plan->sddmm_perm ? 4LL * plan->num_pairs : 0) +
+            (plan->weight_perm ? 4LL * plan->num_pairs : 0) +
             (plan->groups ? 16LL * plan->num_groups : 0);
   info[5] = plan->num_pairs;
   info[6] = plan->device;
@@ -148,6 +148,10 @@ int tcgnn_spmm_f32_ex(tcgnn_plan* plan, const float* x, int64_t ldx, const float
     set_last_error("tcgnn_spmm_f32: ldy < dim");
     return TCGNN_ERR_INVALID_ARG;
   }
+  if ((flags & TCGNN_W_TILE_ORDER) && edge_weight == nullptr) {
+    set_last_error("tcgnn_spmm_f32: TCGNN_W_TILE_ORDER without a weight array");
+    return TCGNN_ERR_INVALID_ARG;
+  }
   return spmm_launch(plan, x, ldx, edge_weight, y, ldy, dim, flags, static_cast<cudaStream_t>(stream));
 }
 
@@ -164,7 +168,74 @@ int tcgnn_spmm_f32_host(tcgnn_plan* plan, const float* x_host, int64_t ldx, cons
     set_last_error("tcgnn_spmm_f32_host: ldy < dim");
     return TCGNN_ERR_INVALID_ARG;
   }
-  return spmm_host_launch(plan, x_host, ldx, edge_weight, y_host, ldy, dim, static_cast<cudaStream_t>(stream));
+  return host_op_launch(plan, kHostSpmm, x_host, ldx, edge_weight, y_host, ldy, nullptr, dim,
+                        static_cast<cudaStream_t>(stream));
+}
+
+int tcgnn_sddmm_f32_host(tcgnn_plan* plan, const float* x_host, int64_t ldx, float* edge_out_host, int32_t dim,
+                         void* stream) {
+  if (plan != nullptr && plan->num_edges == 0) return TCGNN_OK;
+  int st = check_op("tcgnn_sddmm_f32_host", plan, x_host, ldx, edge_out_host, dim);
+  if (st != TCGNN_OK) return st;
+  return host_op_launch(plan, kHostSddmm, x_host, ldx, nullptr, nullptr, 0, edge_out_host, dim,
+                        static_cast<cudaStream_t>(stream));
+}
+
+int tcgnn_agnn_f32_host(tcgnn_plan* plan, const float* x_host, int64_t ldx, const float* attention_w, float* y_host,
+                        int64_t ldy, float* edge_out_host, int32_t dim, void* stream) {
+  int st = check_op("tcgnn_agnn_f32_host", plan, x_host, ldx, y_host, dim);
+  if (st != TCGNN_OK) return st;
+  if (ldy < dim) {
+    set_last_error("tcgnn_agnn_f32_host: ldy < dim");
+    return TCGNN_ERR_INVALID_ARG;
+  }
+  return host_op_launch(plan, kHostAgnn, x_host, ldx, attention_w, y_host, ldy, edge_out_host, dim,
+                        static_cast<cudaStream_t>(stream));
+}
+
+int tcgnn_agnn_f32(tcgnn_plan* plan, const float* x, int64_t ldx, const float* attention_w, float* y, int64_t ldy,
+                   float* att_tile_out, float* edge_out, int32_t dim, uint32_t flags, void* stream) {
+  int st = check_op("tcgnn_agnn_f32", plan, x, ldx, y, dim);
+  if (st != TCGNN_OK) return st;
+  if (plan->row_base < 0) {
+    set_last_error("tcgnn_agnn_f32: the plan was created with row_base = -1 (its rows are not rows of X): SpMM only");
+    return TCGNN_ERR_INVALID_ARG;
+  }
+  if (ldy < dim) {
+    set_last_error("tcgnn_agnn_f32: ldy < dim");
+    return TCGNN_ERR_INVALID_ARG;
+  }
+  return agnn_launch(plan, x, ldx, attention_w, y, ldy, att_tile_out, edge_out, dim, flags & TCGNN_X_IS_TF32,
+                     static_cast<cudaStream_t>(stream));
+}
+
+int tcgnn_csr_transpose(const int32_t* row_ptr, const int32_t* col_idx, int32_t num_rows, int32_t num_cols,
+                        int64_t num_edges, int32_t* row_ptr_t, int32_t* col_idx_t, int32_t* edge_map_t, void* stream) {
+  if (row_ptr == nullptr || row_ptr_t == nullptr || num_rows < 0 || num_cols < 0 || num_edges < 0 ||
+      num_edges > 0x7FFFFFFFLL || (num_edges > 0 && (col_idx == nullptr || col_idx_t == nullptr))) {
+    set_last_error("tcgnn_csr_transpose: bad argument");
+    return TCGNN_ERR_INVALID_ARG;
+  }
+  return csr_transpose_launch(row_ptr, col_idx, num_rows, num_cols, num_edges, row_ptr_t, col_idx_t, edge_map_t,
+                              static_cast<cudaStream_t>(stream));
+}
+
+int tcgnn_gather_rows(const float* src, int64_t ld, const int32_t* rows, int64_t n_rows, float* dst, void* stream) {
+  if (n_rows < 0 || ld < 4 || (ld & 3) != 0 ||
+      (n_rows > 0 && (src == nullptr || rows == nullptr || dst == nullptr ||
+                      (reinterpret_cast<uintptr_t>(src) & 15) != 0 || (reinterpret_cast<uintptr_t>(dst) & 15) != 0))) {
+    set_last_error("tcgnn_gather_rows: bad argument (ld %% 4 == 0, 16-byte aligned src / dst)");
+    return TCGNN_ERR_INVALID_ARG;
+  }
+  return gather_rows_launch(src, ld, rows, n_rows, dst, static_cast<cudaStream_t>(stream));
+}
+
+int tcgnn_stream_wait_flag(const int32_t* flag, int32_t value, int32_t timeout_ms, int32_t* error_out, void* stream) {
+  if (flag == nullptr || (reinterpret_cast<uintptr_t>(flag) & 3) != 0) {
+    set_last_error("tcgnn_stream_wait_flag: flag is null or misaligned");
+    return TCGNN_ERR_INVALID_ARG;
+  }
+  return wait_flag_launch(flag, value, timeout_ms, error_out, static_cast<cudaStream_t>(stream));
 }
 
 int tcgnn_sddmm_f32_ex(tcgnn_plan* plan, const float* x, int64_t ldx, float* edge_out, int32_t dim, uint32_t flags,
@@ -172,7 +243,12 @@ int tcgnn_sddmm_f32_ex(tcgnn_plan* plan, const float* x, int64_t ldx, float* edg
   if (plan != nullptr && plan->num_edges == 0) return TCGNN_OK;
   int st = check_op("tcgnn_sddmm_f32", plan, x, ldx, edge_out, dim);
   if (st != TCGNN_OK) return st;
-  return sddmm_launch(plan, x, ldx, edge_out, dim, flags, static_cast<cudaStream_t>(stream));
+  if (plan->row_base < 0) {
+    set_last_error("tcgnn_sddmm_f32: the plan was created with row_base = -1 (its rows are not rows of X): SpMM only");
+    return TCGNN_ERR_INVALID_ARG;
+  }
+  return sddmm_launch(plan, x, ldx, edge_out, nullptr, nullptr, dim, flags & TCGNN_X_IS_TF32,
+                      static_cast<cudaStream_t>(stream));
 }
 
 int tcgnn_sddmm_f32(tcgnn_plan* plan, const float* x, int64_t ldx, float* edge_out, int32_t dim, void* stream) {

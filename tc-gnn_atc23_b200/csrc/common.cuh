@@ -4,6 +4,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
 
 #include "../../include/tcgnn_b200.h"
 
@@ -129,14 +130,32 @@ __device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Wait with a watchdog: a protocol bug must surface as a launch failure, never as a hung GPU.
+// Wait with a watchdog: a protocol bug must surface as a launch failure, never as a hung GPU.  The limit is
+// wall-clock (globaltimer), far above anything a correct pipeline waits for even when the context is time-sliced
+// or runs under a debugger / sanitizer; -DTCGNN_WATCHDOG_NS=0 compiles it out.  Before trapping it says why, so
+// the host sees "pipeline watchdog" next to the sticky launch failure.
+#ifndef TCGNN_WATCHDOG_NS
+#define TCGNN_WATCHDOG_NS 30000000000ULL   // 30 s
+#endif
+__device__ __forceinline__ uint64_t global_timer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+static __device__ __noinline__ void watchdog_trap(uint32_t bar, uint32_t parity) {
+  printf("tcgnn: pipeline watchdog -- block %d thread %d waited > %llu ms on mbarrier 0x%x (parity %u)\n", blockIdx.x,
+         threadIdx.x, static_cast<unsigned long long>(TCGNN_WATCHDOG_NS / 1000000ULL), bar, parity);
+  asm volatile("trap;");
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
+  uint64_t t0 = 0;
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if ((++spins & 0x3FFu) == 0 && clock64() - t0 > 4000000000LL) {  // ~2 s at 1.9 GHz
-      asm volatile("trap;");
+    if (TCGNN_WATCHDOG_NS != 0 && (++spins & 0xFFFu) == 0) {
+      const uint64_t now = global_timer_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > TCGNN_WATCHDOG_NS) watchdog_trap(bar, parity);
     }
   }
 }
@@ -144,12 +163,14 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 // compete for issue slots and shared-memory bandwidth with the warps on the critical path.
 __device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
+  uint64_t t0 = 0;
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
     __nanosleep(64);
-    if ((++spins & 0x3FFu) == 0 && clock64() - t0 > 4000000000LL) {
-      asm volatile("trap;");
+    if (TCGNN_WATCHDOG_NS != 0 && (++spins & 0xFFFu) == 0) {
+      const uint64_t now = global_timer_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > TCGNN_WATCHDOG_NS) watchdog_trap(bar, parity);
     }
   }
 }

@@ -9,60 +9,9 @@
 
 #include <new>
 
-#include "plan.h"
+#include "scan.cuh"
 
 namespace tcgnn {
-
-// ------------------------------------------------------------------------------------------
-// exclusive scan of int32 (three-pass: block sums -> scan of sums -> add back)
-// ------------------------------------------------------------------------------------------
-constexpr int kScanThreads = 256;
-constexpr int kScanItems = 16;
-constexpr int kScanTile = kScanThreads * kScanItems;
-
-template <typename Load>
-__device__ __forceinline__ void block_scan_tile(Load load, int64_t n, int64_t base, int32_t* out, int32_t carry_in,
-                                                int32_t* tile_total) {
-  __shared__ int32_t warp_sums[kScanThreads / 32];
-  const int tid = threadIdx.x;
-  int32_t vals[kScanItems];
-  int32_t thread_sum = 0;
-  const int64_t first = base + static_cast<int64_t>(tid) * kScanItems;
-#pragma unroll
-  for (int i = 0; i < kScanItems; ++i) {
-    const int64_t idx = first + i;
-    vals[i] = idx < n ? load(idx) : 0;
-    thread_sum += vals[i];
-  }
-  // warp inclusive scan of thread sums
-  int32_t incl = thread_sum;
-#pragma unroll
-  for (int ofs = 1; ofs < 32; ofs <<= 1) {
-    int32_t t = __shfl_up_sync(0xffffffffu, incl, ofs);
-    if ((tid & 31) >= ofs) incl += t;
-  }
-  if ((tid & 31) == 31) warp_sums[tid >> 5] = incl;
-  __syncthreads();
-  int32_t warp_prefix = 0;
-  int32_t total = 0;
-#pragma unroll
-  for (int w = 0; w < kScanThreads / 32; ++w) {
-    const int32_t s = warp_sums[w];
-    if (w < (tid >> 5)) warp_prefix += s;
-    total += s;
-  }
-  if (out != nullptr) {
-    int32_t run = carry_in + warp_prefix + incl - thread_sum;
-#pragma unroll
-    for (int i = 0; i < kScanItems; ++i) {
-      const int64_t idx = first + i;
-      if (idx < n) out[idx] = run;
-      run += vals[i];
-    }
-  }
-  if (tile_total != nullptr && tid == 0) *tile_total = total;
-  __syncthreads();
-}
 
 struct LoadClampedBp {  // max(blockPartition[w], 1): a window always owns at least one tile
   const int32_t* bp;
@@ -79,51 +28,6 @@ struct LoadTilePopc {
     return __popc(m.x) + __popc(m.y) + __popc(m.z) + __popc(m.w);
   }
 };
-
-template <typename Load>
-__global__ void __launch_bounds__(kScanThreads) scan_block_sums(Load load, int64_t n, int32_t* block_sums) {
-  block_scan_tile(load, n, static_cast<int64_t>(blockIdx.x) * kScanTile, nullptr, 0, &block_sums[blockIdx.x]);
-}
-// single block: exclusive scan of block sums in place; writes the grand total to sums[nblocks]
-__global__ void __launch_bounds__(kScanThreads) scan_sums_inplace(int32_t* sums, int32_t nblocks) {
-  __shared__ int32_t carry;
-  __shared__ int32_t tile_total;
-  if (threadIdx.x == 0) carry = 0;
-  __syncthreads();
-  struct L {
-    const int32_t* p;
-    __device__ int32_t operator()(int64_t i) const { return p[i]; }
-  } load{sums};
-  for (int64_t base = 0; base < nblocks; base += kScanTile) {
-    const int32_t c = carry;
-    block_scan_tile(load, nblocks, base, sums, c, &tile_total);
-    if (threadIdx.x == 0) carry = c + tile_total;
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) sums[nblocks] = carry;
-}
-template <typename Load>
-__global__ void __launch_bounds__(kScanThreads) scan_apply(Load load, int64_t n, const int32_t* block_offsets,
-                                                          int32_t* out) {
-  block_scan_tile(load, n, static_cast<int64_t>(blockIdx.x) * kScanTile, out, block_offsets[blockIdx.x], nullptr);
-}
-
-// out[0..n) = exclusive scan, out[n] = total (also left in scratch[nblocks]).
-template <typename Load>
-static cudaError_t exclusive_scan(Load load, int64_t n, int32_t* out, int32_t* scratch, cudaStream_t stream) {
-  const int nblocks = static_cast<int>((n + kScanTile - 1) / kScanTile);
-  if (nblocks > 0) {
-    scan_block_sums<<<nblocks, kScanThreads, 0, stream>>>(load, n, scratch);
-    count_launch();
-  }
-  scan_sums_inplace<<<1, kScanThreads, 0, stream>>>(scratch, nblocks);
-  count_launch();
-  if (nblocks > 0) {
-    scan_apply<<<nblocks, kScanThreads, 0, stream>>>(load, n, scratch, out);
-    count_launch();
-  }
-  return cudaMemcpyAsync(out + n, scratch + nblocks, sizeof(int32_t), cudaMemcpyDeviceToDevice, stream);
-}
 
 // ------------------------------------------------------------------------------------------
 // tile records
@@ -175,20 +79,35 @@ __global__ void scatter_edges_kernel(TileMeta* tiles, const int32_t* __restrict_
 // Tile range of every persistent CTA.  A CTA's time is ~ a * tiles + b * windows (every window costs an
 // accumulator hand-over and a 16 x D output tile; measured b / a = 4..14, profiles/r01e_*), so slices are
 // balanced on tiles + win_cost * windows, not on tiles alone: R-MAT graphs have long runs of 1-tile windows.
-__global__ void slice_bounds_kernel(const TileMeta* __restrict__ tiles, int32_t num_tiles, int32_t num_windows,
-                                    int32_t win_cost, int32_t grid, int32_t* __restrict__ slice_ptr) {
+// blockIdx.y = chunk: the tiles of the windows [win_bounds[c], win_bounds[c+1]) (one chunk = the whole plan when
+// win_bounds is null) are cut into `grid` slices; slice_ptr is [chunks][grid + 1].
+__global__ void slice_bounds_kernel(const TileMeta* __restrict__ tiles, const int32_t* __restrict__ win_tile_ptr,
+                                    const int32_t* __restrict__ win_bounds, int32_t num_windows, int32_t win_cost,
+                                    int32_t grid, int32_t* __restrict__ slice_ptr) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i > grid) return;
-  const int64_t total = static_cast<int64_t>(num_tiles) + static_cast<int64_t>(win_cost) * num_windows;
+  const int32_t w_lo = win_bounds ? win_bounds[blockIdx.y] : 0;
+  const int32_t w_hi = win_bounds ? win_bounds[blockIdx.y + 1] : num_windows;
+  const int32_t t_lo = win_tile_ptr[w_lo], t_hi = win_tile_ptr[w_hi];
+  const int64_t total = static_cast<int64_t>(t_hi - t_lo) + static_cast<int64_t>(win_cost) * (w_hi - w_lo);
   const int64_t target = total * i / grid;
-  // smallest t with cost(t) = t + win_cost * (windows begun before tile t) >= target
-  int32_t lo = 0, hi = num_tiles;
+  // smallest t with cost(t) = (t - t_lo) + win_cost * (windows begun before tile t) >= target
+  int32_t lo = t_lo, hi = t_hi;
   while (lo < hi) {
     const int32_t mid = lo + (hi - lo) / 2;
-    const int64_t cost = mid + static_cast<int64_t>(win_cost) * tiles[mid].win;
+    const int64_t cost = (mid - t_lo) + static_cast<int64_t>(win_cost) * (tiles[mid].win - w_lo);
     if (cost >= target) hi = mid; else lo = mid + 1;
   }
-  slice_ptr[i] = i == grid ? num_tiles : (i == 0 ? 0 : lo);
+  slice_ptr[static_cast<int64_t>(blockIdx.y) * (grid + 1) + i] = i == grid ? t_hi : (i == 0 ? t_lo : lo);
+}
+
+static int window_cost() {
+  static const int win_cost = [] {
+    const char* e = getenv("TCGNN_WIN_COST");
+    const int v = e ? atoi(e) : 3;
+    return v < 0 ? 0 : (v > 64 ? 64 : v);
+  }();
+  return win_cost;
 }
 
 __global__ void store_edge_ofs_kernel(TileMeta* tiles, const int32_t* __restrict__ tile_ofs, int32_t num_tiles) {
@@ -324,14 +243,9 @@ int plan_create(const int32_t* row_ptr, const int32_t* col_idx, const int32_t* b
     p->grid = p->num_sms;
     if (p->num_tiles < p->grid * 8) p->grid = p->num_tiles / 8;
     if (p->grid < 1) p->grid = 1;
-    static const int win_cost = [] {
-      const char* e = getenv("TCGNN_WIN_COST");
-      const int v = e ? atoi(e) : 3;
-      return v < 0 ? 0 : (v > 64 ? 64 : v);
-    }();
     PLAN_CUDA(cudaMalloc(&p->slice_ptr, sizeof(int32_t) * (static_cast<size_t>(p->grid) + 1)));
-    slice_bounds_kernel<<<(p->grid + 256) / 256, 256, 0, stream>>>(p->tiles, p->num_tiles, num_windows, win_cost,
-                                                                   p->grid, p->slice_ptr);
+    slice_bounds_kernel<<<(p->grid + 256) / 256, 256, 0, stream>>>(p->tiles, p->win_tile_ptr, nullptr, num_windows,
+                                                                   window_cost(), p->grid, p->slice_ptr);
     count_launch();
     PLAN_CUDA(cudaGetLastError());
     PLAN_CUDA(cudaStreamSynchronize(stream));
@@ -424,101 +338,54 @@ int plan_ensure_scratch(tcgnn_plan* p, float** slot, size_t count) {
   return TCGNN_OK;
 }
 
-// SpMM with HOST feature / result buffers (pinned memory for full speed): host -> device copy of X, the kernels
-// and the device -> host copy of Y on the plan's copy streams and the caller's stream.  Ordered on `stream`: work queued before the call is waited for, and `stream`
-// waits for the last copy, so a later cudaStreamSynchronize(stream) / event covers y_host.
-int spmm_host_launch(tcgnn_plan* p, const float* x_host, int64_t ldx, const float* edge_weight, float* y_host,
-                     int64_t ldy, int32_t dim, cudaStream_t stream) {
-  const size_t need_x = static_cast<size_t>(p->num_cols) * dim, need_y = static_cast<size_t>(p->num_nodes) * dim;
-  {
-    std::lock_guard<std::mutex> lock(p->mu);
-    cudaError_t e = cudaSuccess;
-    if (p->h2d_stream == nullptr) {
-      e = cudaStreamCreateWithFlags(&p->h2d_stream, cudaStreamNonBlocking);
-      if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p->d2h_stream, cudaStreamNonBlocking);
-      for (int i = 0; e == cudaSuccess && i < 6; ++i) e = cudaEventCreateWithFlags(&p->host_ev[i], cudaEventDisableTiming);
-    }
-    if (e == cudaSuccess && (p->host_x_cap < need_x || p->host_y_cap < need_y)) {
-      e = cudaStreamSynchronize(stream);   // the old staging buffers may still be in use
-      if (e == cudaSuccess && p->host_x_cap < need_x) {
-        if (p->host_x_dev) cudaFree(p->host_x_dev);
-        p->host_x_dev = nullptr;
-        p->host_x_cap = 0;
-        e = cudaMalloc(&p->host_x_dev, need_x * sizeof(float));
-        if (e == cudaSuccess) p->host_x_cap = need_x;
-      }
-      if (e == cudaSuccess && p->host_y_cap < need_y) {
-        if (p->host_y_dev) cudaFree(p->host_y_dev);
-        p->host_y_dev = nullptr;
-        p->host_y_cap = 0;
-        e = cudaMalloc(&p->host_y_dev, need_y * sizeof(float));
-        if (e == cudaSuccess) p->host_y_cap = need_y;
-      }
-    }
-    if (e != cudaSuccess) {
-      set_last_error("tcgnn_spmm_f32_host: staging setup failed: %s", cudaGetErrorString(e));
-      return e == cudaErrorMemoryAllocation ? TCGNN_ERR_OOM : TCGNN_ERR_CUDA;
-    }
+int plan_set_row_chunks(tcgnn_plan* p, const int32_t* win_bounds, int n_chunks, cudaStream_t stream) {
+  if (n_chunks < 1 || win_bounds == nullptr || win_bounds[0] != 0 || win_bounds[n_chunks] != p->num_windows) {
+    set_last_error("plan_set_row_chunks: bounds must run from 0 to num_windows");
+    return TCGNN_ERR_INVALID_ARG;
   }
-  // One chunk.  Pipelining over two feature-column chunks (SpMM is independent per column) was measured and
-  // rejected: the column halves are strided on the host side, and 256-byte-row cudaMemcpy2DAsync transfers ran at
-  // ~15 GB/s instead of ~57 GB/s (e2e 18.0 ms vs 7.4 ms on the reddit-sized graph, profiles/r01j_*).
-  const int nchunk = 1;
-  const int32_t wc = dim / nchunk;
-  cudaEvent_t* ev = p->host_ev;
-  int status = TCGNN_OK;
-#define HOST_CUDA(expr)                                                                    \
-  do {                                                                                     \
-    cudaError_t _e = (expr);                                                               \
-    if (_e != cudaSuccess) {                                                               \
-      set_last_error("tcgnn_spmm_f32_host: %s failed: %s", #expr, cudaGetErrorString(_e)); \
-      return TCGNN_ERR_CUDA;                                                               \
-    }                                                                                      \
-  } while (0)
-  HOST_CUDA(cudaEventRecord(ev[0], stream));
-  HOST_CUDA(cudaStreamWaitEvent(p->h2d_stream, ev[0], 0));
-  HOST_CUDA(cudaStreamWaitEvent(p->d2h_stream, ev[0], 0));
-  for (int c = 0; c < nchunk; ++c) {
-    float* xd = p->host_x_dev + static_cast<size_t>(p->num_cols) * wc * c;
-    if (ldx == wc) {
-      HOST_CUDA(cudaMemcpyAsync(xd, x_host, sizeof(float) * need_x, cudaMemcpyHostToDevice, p->h2d_stream));
-    } else {
-      HOST_CUDA(cudaMemcpy2DAsync(xd, sizeof(float) * wc, x_host + static_cast<size_t>(wc) * c, sizeof(float) * ldx,
-                                  sizeof(float) * wc, static_cast<size_t>(p->num_cols), cudaMemcpyHostToDevice,
-                                  p->h2d_stream));
+  for (int r = 0; r < n_chunks; ++r)
+    if (win_bounds[r + 1] < win_bounds[r]) {
+      set_last_error("plan_set_row_chunks: bounds must be non-decreasing");
+      return TCGNN_ERR_INVALID_ARG;
     }
-    HOST_CUDA(cudaEventRecord(ev[1 + c], p->h2d_stream));
+  std::lock_guard<std::mutex> lock(p->mu);
+  int32_t* d_bounds = nullptr;
+  int32_t* table = nullptr;
+  cudaError_t e = cudaMalloc(&d_bounds, sizeof(int32_t) * (n_chunks + 1));
+  if (e == cudaSuccess) e = cudaMalloc(&table, sizeof(int32_t) * static_cast<size_t>(n_chunks) * (p->grid + 1));
+  if (e == cudaSuccess)
+    e = cudaMemcpyAsync(d_bounds, win_bounds, sizeof(int32_t) * (n_chunks + 1), cudaMemcpyHostToDevice, stream);
+  if (e == cudaSuccess) {
+    slice_bounds_kernel<<<dim3((p->grid + 256) / 256, n_chunks), 256, 0, stream>>>(
+        p->tiles, p->win_tile_ptr, d_bounds, p->num_windows, window_cost(), p->grid, table);
+    count_launch();
+    e = cudaGetLastError();
   }
-  for (int c = 0; c < nchunk; ++c) {
-    const float* xd = p->host_x_dev + static_cast<size_t>(p->num_cols) * wc * c;
-    float* yd = p->host_y_dev + static_cast<size_t>(p->num_nodes) * wc * c;
-    HOST_CUDA(cudaStreamWaitEvent(stream, ev[1 + c], 0));
-    status = spmm_launch(p, xd, wc, edge_weight, yd, wc, wc, 0u, stream);
-    if (status != TCGNN_OK) return status;
-    HOST_CUDA(cudaEventRecord(ev[3 + c], stream));
-    HOST_CUDA(cudaStreamWaitEvent(p->d2h_stream, ev[3 + c], 0));
-    if (ldy == wc) {
-      HOST_CUDA(cudaMemcpyAsync(y_host, yd, sizeof(float) * need_y, cudaMemcpyDeviceToHost, p->d2h_stream));
-    } else {
-      HOST_CUDA(cudaMemcpy2DAsync(y_host + static_cast<size_t>(wc) * c, sizeof(float) * ldy, yd, sizeof(float) * wc,
-                                  sizeof(float) * wc, static_cast<size_t>(p->num_nodes), cudaMemcpyDeviceToHost,
-                                  p->d2h_stream));
-    }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(stream);   // win_bounds is the caller's (pageable) memory
+  if (d_bounds) cudaFree(d_bounds);
+  if (e != cudaSuccess) {
+    if (table) cudaFree(table);
+    set_last_error("plan_set_row_chunks failed: %s", cudaGetErrorString(e));
+    return e == cudaErrorMemoryAllocation ? TCGNN_ERR_OOM : TCGNN_ERR_CUDA;
   }
-  HOST_CUDA(cudaEventRecord(ev[5], p->d2h_stream));
-  HOST_CUDA(cudaStreamWaitEvent(stream, ev[5], 0));
-#undef HOST_CUDA
+  if (p->chunk_slice_ptr) cudaFree(p->chunk_slice_ptr);
+  p->chunk_slice_ptr = table;
+  p->row_chunk_win.assign(win_bounds, win_bounds + n_chunks + 1);
   return TCGNN_OK;
 }
 
 int plan_destroy(tcgnn_plan* p) {
   if (p == nullptr) return TCGNN_OK;
+  for (tcgnn_plan* c : p->col_chunks) plan_destroy(c);
+  for (void* a : p->owned)
+    if (a) cudaFree(a);
+  if (p->chunk_slice_ptr) cudaFree(p->chunk_slice_ptr);
+  if (p->host_e_dev) cudaFree(p->host_e_dev);
   if (p->tiles) cudaFree(p->tiles);
   if (p->win_tile_ptr) cudaFree(p->win_tile_ptr);
   if (p->slice_ptr) cudaFree(p->slice_ptr);
   if (p->eperm) cudaFree(p->eperm);
   if (p->weight_perm) cudaFree(p->weight_perm);
-  if (p->sddmm_perm) cudaFree(p->sddmm_perm);
   if (p->x_round) cudaFree(p->x_round);
   if (p->groups) cudaFree(p->groups);
   if (p->flag) cudaFree(p->flag);

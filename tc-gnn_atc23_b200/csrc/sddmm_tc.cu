@@ -62,7 +62,9 @@ constexpr uint32_t kTuneXLast = 16u;                       // env TCGNN_TUNE: ga
 __global__ void __launch_bounds__(kThreads, 1)
 sddmm_tc_kernel(PlanView pv, const int4* __restrict__ groups, int32_t num_groups,
                 const float* __restrict__ x /* tf32-rounded, 16B aligned */, int64_t ldx /* % 4 == 0 */,
-                float* __restrict__ out_perm, int32_t dim, uint32_t flags) {
+                float* __restrict__ out_csr /* nullable: CSR edge order (via eperm) */,
+                float* __restrict__ out_tile /* nullable: tile order, tf32_rna(score * *scale) */,
+                const float* __restrict__ scale /* nullable (1.0); device scalar */, int32_t dim, uint32_t flags) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_smem = smem;
@@ -118,6 +120,7 @@ sddmm_tc_kernel(PlanView pv, const int4* __restrict__ groups, int32_t num_groups
     const int m = q * 32 + lane;       // condensed column inside the group
     const int tt = m >> 3, c = m & 7;  // tile inside the group, column inside the tile
     const int tid = threadIdx.x;       // 0..127
+    const float att_scale = scale != nullptr ? __ldg(scale) : 1.0f;
     for (int32_t gl = 0; gl < n_groups; ++gl) {
       const int4 grp = groups[g_lo + gl];
       uint4 mask = make_uint4(0, 0, 0, 0);
@@ -160,7 +163,14 @@ sddmm_tc_kernel(PlanView pv, const int4* __restrict__ groups, int32_t num_groups
       // double-buffered: the barrier of group gl also orders everybody's reads of group gl-1's buffer before
       // the writes of group gl+1 into it
       named_barrier_sync(1, kEpiWarps * 32);
-      for (int i = tid; i < n_out; i += kEpiWarps * 32) out_perm[e0 + i] = __uint_as_float(lds_u32(obuf + i * 4));
+      // CSR order straight from here (one coalesced read of the tile-order -> edge-id map, stores in runs of the
+      // <= 8 consecutive edges a row has inside a tile) -- no second pass over the [E] array; the fused AGNN
+      // path also / only leaves the scaled, tf32-rounded attention in tile order for the weighted SpMM.
+      for (int i = tid; i < n_out; i += kEpiWarps * 32) {
+        const float v = __uint_as_float(lds_u32(obuf + i * 4));
+        if (out_csr != nullptr) out_csr[__ldg(pv.eperm + e0 + i)] = v;
+        if (out_tile != nullptr) out_tile[e0 + i] = tf32_rna(v * att_scale);
+      }
     }
   } else if (warp == kMmaWarp) {
     // ===================================== MMA issuer ===================================
@@ -299,64 +309,51 @@ sddmm_tc_kernel(PlanView pv, const int4* __restrict__ groups, int32_t num_groups
   }
 }
 
-// tile order -> CSR edge order
-__global__ void unpermute_kernel(const int32_t* __restrict__ eperm, const float* __restrict__ in,
-                                 float* __restrict__ out, int32_t n) {
-  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
-       i += static_cast<int64_t>(gridDim.x) * blockDim.x)
-    out[eperm[i]] = in[i];
-}
-
 }  // namespace
 
-int sddmm_launch(tcgnn_plan* plan, const float* x, int64_t ldx, float* edge_out, int32_t dim, uint32_t op_flags,
-                 cudaStream_t stream) {
+// edge_out_csr (nullable): scores in CSR edge order.  tile_out (nullable): tf32_rna(score * *scale) in the plan's
+// tile order -- the weight operand of spmm_launch(TCGNN_W_TILE_ORDER).
+int sddmm_launch(tcgnn_plan* plan, const float* x, int64_t ldx, float* edge_out_csr, float* tile_out,
+                 const float* scale, int32_t dim, uint32_t op_flags, cudaStream_t stream) {
   if (plan->num_edges == 0) return TCGNN_OK;
-  int st = plan_ensure_eperm(plan, stream);
+  int st = edge_out_csr != nullptr ? plan_ensure_eperm(plan, stream) : TCGNN_OK;
   if (st != TCGNN_OK) return st;
   st = plan_ensure_groups(plan, stream);
   if (st != TCGNN_OK) return st;
-  st = plan_ensure_scratch(plan, &plan->sddmm_perm, static_cast<size_t>(plan->num_pairs));
-  if (st != TCGNN_OK) return st;
+  static std::mutex attr_mu;
   static bool attr_set[64] = {};
   cudaError_t e;
-  if (plan->device < 64 && !attr_set[plan->device]) {
-    e = cudaFuncSetAttribute(sddmm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-    if (e != cudaSuccess) {
-      set_last_error("cudaFuncSetAttribute(sddmm) failed: %s", cudaGetErrorString(e));
-      return TCGNN_ERR_CUDA;
+  {
+    std::lock_guard<std::mutex> lock(attr_mu);
+    if (plan->device >= 64 || !attr_set[plan->device]) {
+      e = cudaFuncSetAttribute(sddmm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+      if (e != cudaSuccess) {
+        set_last_error("cudaFuncSetAttribute(sddmm) failed: %s", cudaGetErrorString(e));
+        return TCGNN_ERR_CUDA;
+      }
+      if (plan->device < 64) attr_set[plan->device] = true;
     }
-    attr_set[plan->device] = true;
   }
   const int grid = plan->grid;
   int64_t ldr = (static_cast<int64_t>(dim) + 3) / 4 * 4;
   const float* xr = nullptr;
-  if ((op_flags & TCGNN_X_IS_TF32) && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (ldx & 3) == 0) {
+  if (x_is_prerounded(x, ldx, dim, op_flags)) {
     xr = x;
     ldr = ldx;
   } else {
     st = round_pack_launch(plan, x, ldx, dim, ldr, stream, &xr);
     if (st != TCGNN_OK) return st;
   }
-  if (static_cast<int64_t>(plan->num_pairs) < plan->num_edges) {
+  if (edge_out_csr != nullptr && static_cast<int64_t>(plan->num_pairs) < plan->num_edges) {
     // duplicated (row, col) pairs: only one edge of each pair receives the value (as in the reference)
-    e = cudaMemsetAsync(edge_out, 0, sizeof(float) * static_cast<size_t>(plan->num_edges), stream);
+    e = cudaMemsetAsync(edge_out_csr, 0, sizeof(float) * static_cast<size_t>(plan->num_edges), stream);
     if (e != cudaSuccess) {
       set_last_error("cudaMemsetAsync failed: %s", cudaGetErrorString(e));
       return TCGNN_ERR_CUDA;
     }
   }
-  static const uint32_t flags = [] {
-    const char* t = getenv("TCGNN_TUNE");
-    return t ? static_cast<uint32_t>(strtoul(t, nullptr, 0)) & kTuneXLast : kTuneXLast;
-  }();
   sddmm_tc_kernel<<<grid, kThreads, kSmemBytes, stream>>>(plan->view(), plan->groups, plan->num_groups, xr, ldr,
-                                                         plan->sddmm_perm, dim, flags);
-  count_launch();
-  int g = (plan->num_pairs + 255) / 256;
-  if (g > 148 * 16) g = 148 * 16;
-  if (g < 1) g = 1;
-  unpermute_kernel<<<g, 256, 0, stream>>>(plan->eperm, plan->sddmm_perm, edge_out, plan->num_pairs);
+                                                         edge_out_csr, tile_out, scale, dim, kTuneXLast);
   count_launch();
   e = cudaGetLastError();
   if (e != cudaSuccess) {
@@ -364,6 +361,39 @@ int sddmm_launch(tcgnn_plan* plan, const float* x, int64_t ldx, float* edge_out,
     return TCGNN_ERR_CUDA;
   }
   return TCGNN_OK;
+}
+
+// Fused AGNN edge pipeline (reference gnn_conv.py:125-132: SDDMM -> x attention_w -> weighted SpMM): the SDDMM
+// epilogue leaves tf32_rna(score * attention_w) in tile order, which is exactly the B-operand stream of the weighted
+// SpMM -- no unpermute / permute passes, no [E] round trip through the caller, X rounded once for both kernels.
+int agnn_launch(tcgnn_plan* plan, const float* x, int64_t ldx, const float* attention_w, float* y, int64_t ldy,
+                float* att_tile_out, float* edge_out_csr, int32_t dim, uint32_t op_flags, cudaStream_t stream) {
+  float* att = att_tile_out;
+  if (att == nullptr) {
+    int st = plan_ensure_scratch(plan, &plan->weight_perm, static_cast<size_t>(plan->num_pairs));
+    if (st != TCGNN_OK) return st;
+    att = plan->weight_perm;
+  }
+  // X is rounded once for both kernels when its width allows 16-byte rows; a ragged width makes each kernel pack
+  // its own zero-padded copy (as the separate entry points do)
+  const float* xr = x;
+  int64_t ldr = ldx;
+  uint32_t flags = op_flags;
+  if (!x_is_prerounded(x, ldx, dim, op_flags)) {
+    flags &= ~TCGNN_X_IS_TF32;
+    if ((dim & 3) == 0) {
+      int st = round_pack_launch(plan, x, ldx, dim, dim, stream, &xr);
+      if (st != TCGNN_OK) return st;
+      ldr = dim;
+      flags |= TCGNN_X_IS_TF32;
+    }
+  }
+  if (plan->num_edges > 0) {
+    int st = sddmm_launch(plan, xr, ldr, edge_out_csr, att, attention_w, dim, flags, stream);
+    if (st != TCGNN_OK) return st;
+  }
+  return spmm_launch(plan, xr, ldr, plan->num_pairs > 0 ? att : nullptr, y, ldy, dim,
+                     (flags & ~TCGNN_ACCUMULATE) | TCGNN_W_TILE_ORDER, stream);
 }
 
 }  // namespace tcgnn

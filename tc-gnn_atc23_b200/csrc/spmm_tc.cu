@@ -54,7 +54,14 @@ constexpr int kMetaWarp = 5;
 constexpr int kProducerWarp0 = 6;     // producer warp p owns the stages p, p + P, ...
 constexpr int kAcc = 4;               // TMEM accumulator ring
 constexpr int kBTileBytes = TCGNN_BLK_H * TCGNN_BLK_W * 4;  // 512
-// ablation switches (env TCGNN_ABLATE, profiling only -- results are wrong when set): skip the row
+// Profiling switches are compiled in only with -DTCGNN_DEBUG_SWITCHES (build.py --debug-switches): the production
+// library ignores TCGNN_ABLATE / TCGNN_TUNE / TCGNN_TRACE / TCGNN_PRESET, and the ablation branches fold away.
+#ifdef TCGNN_DEBUG_SWITCHES
+constexpr bool kDebugSwitches = true;
+#else
+constexpr bool kDebugSwitches = false;
+#endif
+// ablation switches (env TCGNN_ABLATE, profiling builds only -- results are wrong when set): skip the row
 // gathers / the MMAs after a window's first / the B-tile construction / all but one MMA of a full stage
 constexpr uint32_t kAblateGather = 1u, kAblateMma = 2u, kAblateBuild = 4u, kAblateMmaFast = 8u;
 constexpr uint32_t kAblateOutput = 256u;   // no bulk output stores
@@ -62,6 +69,9 @@ constexpr uint32_t kAblateOutput = 256u;   // no bulk output stores
 // tile stream evict_first / output rows written with streaming stores
 constexpr uint32_t kTuneXLast = 16u, kTuneMetaFirst = 32u, kTuneYStream = 64u;
 constexpr uint32_t kTuneDefault = kTuneXLast | kTuneMetaFirst | kTuneYStream;
+// op mode (not a debug switch): Y += A X -- every window is combined with the bulk reduce-add / fp32 atomics and
+// nothing is cleared first (TCGNN_ACCUMULATE: per-source-panel partial products of the sharded path)
+constexpr uint32_t kFlagAccumulate = 1u << 24;
 
 // DBLK: 128-feature blocks per pass; G: tiles per pipeline stage; S: data stages; P: producer warps;
 // L: own stages a producer warp keeps in flight before it publishes the oldest
@@ -179,7 +189,7 @@ spmm_tc_kernel(PlanView pv, const float* __restrict__ x /* tf32-rounded, 16B ali
   const SliceInfo sl = slice_info(pv);
   const int32_t n_tiles = sl.t1 - sl.t0;
   const int32_t n_stages = (n_tiles + kG - 1) / kG;
-  const bool tr = trace != nullptr && blockIdx.x == ((flags >> 16) & 0xFFu);   // env TCGNN_TRACE_CTA
+  const bool tr = kDebugSwitches && trace != nullptr && blockIdx.x == ((flags >> 16) & 0xFFu);   // env TCGNN_TRACE_CTA
   const long long t_start = clock64();
 
   if (threadIdx.x == 0) {
@@ -224,7 +234,8 @@ spmm_tc_kernel(PlanView pv, const float* __restrict__ x /* tf32-rounded, 16B ali
       tc_fence_after();
       if (tre && lane == 0) trow[1] = clock64();
       const int32_t w = sl.w_first + wl;
-      const bool use_atomic = (wl == 0 && sl.partial_first) || (wl == sl.n_windows - 1 && sl.partial_last);
+      const bool use_atomic = (flags & kFlagAccumulate) != 0 || (wl == 0 && sl.partial_first) ||
+                              (wl == sl.n_windows - 1 && sl.partial_last);
       const int32_t row0 = w * TCGNN_BLK_H;
       const uint32_t ybuf = y_smem + (wl & 1) * C::kYStageBytes;
 #pragma unroll
@@ -262,7 +273,7 @@ spmm_tc_kernel(PlanView pv, const float* __restrict__ x /* tf32-rounded, 16B ali
         // the copies of window wl-1 have read the other buffer: after the barrier everybody may overwrite it
         if (issuer) tma_bulk_wait_group_read<0>();
         named_barrier_sync(1, kEpiWarps * 32);
-        if (issuer && !(flags & kAblateOutput)) {
+        if (issuer && !(kDebugSwitches && (flags & kAblateOutput))) {
           const int rows = min(TCGNN_BLK_H, pv.num_nodes - row0);
           float* yp = y + static_cast<int64_t>(row0) * ldy;
           // contiguous output: the window's rows are one block (a bulk copy costs ~200 cycles whatever its size)
@@ -284,7 +295,7 @@ spmm_tc_kernel(PlanView pv, const float* __restrict__ x /* tf32-rounded, 16B ali
     const uint64_t adesc0 = make_smem_desc(0, 1024, 512, kSwizzle128BBase32B);
     // B: K-major, no swizzle: 8x16B core matrices; K chunks 128 B apart (LBO), 8-row groups 256 B apart (SBO)
     const uint64_t bdesc0 = make_smem_desc(0, 128, 256, kSwizzleNone);
-    const bool skip_mma = (flags & kAblateMma) != 0;
+    const bool skip_mma = kDebugSwitches && (flags & kAblateMma) != 0;
     int32_t wl = 0;        // windows opened so far
     uint32_t acc = tmem_base;
     int b = 0;
@@ -306,7 +317,7 @@ spmm_tc_kernel(PlanView pv, const float* __restrict__ x /* tf32-rounded, 16B ali
         if (elect_one()) {
 #pragma unroll
           for (int j = 0; j < kG; ++j) {
-            if (j > 0 && (flags & kAblateMmaFast)) break;
+            if (kDebugSwitches && j > 0 && (flags & kAblateMmaFast)) break;
 #pragma unroll
             for (int m = 0; m < DBLK; ++m)
               umma_tf32(acc + m * 16, adesc_s + static_cast<uint64_t>((j * C::kATileBytes + m * 4096) >> 4),
@@ -368,8 +379,8 @@ spmm_tc_kernel(PlanView pv, const float* __restrict__ x /* tf32-rounded, 16B ali
     const int p = warp - kProducerWarp0;
     const int nvec = (dim + 3) >> 2;          // 16-byte vectors per feature row in this pass
     constexpr int kVecPerLane = DBLK * 8;     // 8 rows x DBLK*32 vectors / 32 lanes
-    const bool skip_gather = (flags & kAblateGather) != 0;
-    const bool skip_build = (flags & kAblateBuild) != 0;
+    const bool skip_gather = kDebugSwitches && (flags & kAblateGather) != 0;
+    const bool skip_build = kDebugSwitches && (flags & kAblateBuild) != 0;
     const uint64_t policy = (flags & kTuneXLast) ? l2_policy_evict_last() : l2_policy_evict_normal();
     // B tile: lane -> 16-byte chunk `lane` of the tile: [n/8][k/4][n%8] x 4 floats (k%4)
     const int bn = (lane >> 4) * 8 + (lane & 7);
@@ -528,7 +539,7 @@ spmm_tc_kernel(PlanView pv, const float* __restrict__ x /* tf32-rounded, 16B ali
   // ===================================== teardown =======================================
   tc_fence_before();
   __syncthreads();
-  if (trace != nullptr && threadIdx.x == 0 && blockIdx.x < kTraceCtas) {
+  if (kDebugSwitches && trace != nullptr && threadIdx.x == 0 && blockIdx.x < kTraceCtas) {
     long long* row = trace + 3 * kTraceStages * 8 + blockIdx.x * 4;
     row[0] = clock64() - t_start;
     row[1] = n_tiles;
@@ -542,6 +553,7 @@ spmm_tc_kernel(PlanView pv, const float* __restrict__ x /* tf32-rounded, 16B ali
 }
 
 uint32_t kernel_flags() {
+  if (!kDebugSwitches) return kTuneDefault;
   static const uint32_t flags = [] {
     const char* a = getenv("TCGNN_ABLATE");
     const char* t = getenv("TCGNN_TUNE");
@@ -555,8 +567,10 @@ uint32_t kernel_flags() {
   return flags;
 }
 
-// TCGNN_TRACE=<path>: after every launch, block 0's timeline is written to <path> (3 roles x 512 stages x 8 int64)
+// TCGNN_TRACE=<path> (profiling builds): after every launch, block 0's timeline is written to <path>
+// (3 roles x 512 stages x 8 int64)
 long long* trace_buffer() {
+  if (!kDebugSwitches) return nullptr;
   static long long* buf = [] {
     long long* p = nullptr;
     if (getenv("TCGNN_TRACE") != nullptr) {
@@ -578,26 +592,33 @@ void trace_dump(const long long* trace, cudaStream_t stream) {
 }
 
 template <class C, int DBLK>
-cudaError_t launch_kernel(const tcgnn_plan* plan, int grid, const float* xr, int64_t ldr, const float* wperm, float* y,
-                          int64_t ldy, int32_t dim, cudaStream_t stream) {
+cudaError_t launch_kernel(const tcgnn_plan* plan, const PlanView& pv, int grid, const float* xr, int64_t ldr,
+                          const float* wperm, float* y, int64_t ldy, int32_t dim, uint32_t mode_flags,
+                          cudaStream_t stream) {
+  // the opt-in to > 48 KB of dynamic shared memory is per device and per kernel instantiation
+  static std::mutex attr_mu;
   static bool attr_set[64] = {};
   const int dev = plan->device;
-  if (dev < 64 && !attr_set[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(spmm_tc_kernel<C, DBLK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         C::kSmemBytes);
-    if (e != cudaSuccess) return e;
-    attr_set[dev] = true;
+  {
+    std::lock_guard<std::mutex> lock(attr_mu);
+    if (dev >= 64 || !attr_set[dev]) {
+      cudaError_t e = cudaFuncSetAttribute(spmm_tc_kernel<C, DBLK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           C::kSmemBytes);
+      if (e != cudaSuccess) return e;
+      if (dev < 64) attr_set[dev] = true;
+    }
   }
   long long* trace = trace_buffer();
-  spmm_tc_kernel<C, DBLK><<<grid, C::kThreads, C::kSmemBytes, stream>>>(plan->view(), xr, ldr, wperm, y, ldy, dim,
-                                                                         kernel_flags(), trace);
+  spmm_tc_kernel<C, DBLK><<<grid, C::kThreads, C::kSmemBytes, stream>>>(pv, xr, ldr, wperm, y, ldy, dim,
+                                                                         kernel_flags() | mode_flags, trace);
   count_launch();
   if (trace != nullptr) trace_dump(trace, stream);
   return cudaGetLastError();
 }
 
-// pipeline shape: env TCGNN_PRESET selects among the compiled variants (tuning; 0 = production)
+// pipeline shape: env TCGNN_PRESET selects among the compiled variants (profiling builds; 0 = production choice)
 int preset_setting() {
+  if (!kDebugSwitches) return 0;
   static const int v = [] {
     const char* e = getenv("TCGNN_PRESET");
     return e ? atoi(e) : 0;
@@ -606,13 +627,17 @@ int preset_setting() {
 }
 
 template <int DBLK>
-cudaError_t launch_pass(const tcgnn_plan* plan, int grid, const float* xr, int64_t ldr, const float* wperm, float* y,
-                        int64_t ldy, int32_t dim, cudaStream_t stream) {
-  spmm_zero_partial_rows<<<grid, 128, 0, stream>>>(plan->view(), y, ldy, dim);
-  count_launch();
+cudaError_t launch_pass(const tcgnn_plan* plan, const PlanView& pv, int grid, const float* xr, int64_t ldr,
+                        const float* wperm, float* y, int64_t ldy, int32_t dim, uint32_t mode_flags,
+                        cudaStream_t stream) {
+  if (!(mode_flags & kFlagAccumulate)) {
+    spmm_zero_partial_rows<<<grid, 128, 0, stream>>>(pv, y, ldy, dim);
+    count_launch();
+  }
   constexpr int T = 8 / DBLK;   // tiles in 32 KB of A
 #define TCGNN_LAUNCH(G, S, P, STAGED) \
-  return launch_kernel<Cfg<DBLK, G, S, P, 1, STAGED>, DBLK>(plan, grid, xr, ldr, wperm, y, ldy, dim, stream)
+  return launch_kernel<Cfg<DBLK, G, S, P, 1, STAGED>, DBLK>(plan, pv, grid, xr, ldr, wperm, y, ldy, dim, mode_flags, \
+                                                            stream)
   // Dense windows (hundreds of tiles each: reddit): the deepest ring, output written straight from registers
   // (rare).  Sparse windows: one output tile every few tiles -- stage it and hand it to the TMA engine; the
   // staging buffers cost one pipeline slot.
@@ -620,10 +645,12 @@ cudaError_t launch_pass(const tcgnn_plan* plan, int grid, const float* xr, int64
   if (preset == 0) preset = static_cast<int64_t>(plan->num_tiles) >= 256LL * plan->num_windows ? 1 : 2;
   switch (preset) {
     case 1: TCGNN_LAUNCH(T, 6, 6, false);
+#ifdef TCGNN_DEBUG_SWITCHES
     case 3: TCGNN_LAUNCH(T - 1, 6, 6, true);
     case 4: TCGNN_LAUNCH(T - 1, 6, 5, true);
     case 5: TCGNN_LAUNCH(T, 5, 4, true);
     case 6: TCGNN_LAUNCH(T, 5, 5, false);
+#endif
     default: TCGNN_LAUNCH(T, 5, 5, true);
   }
 #undef TCGNN_LAUNCH
@@ -631,24 +658,38 @@ cudaError_t launch_pass(const tcgnn_plan* plan, int grid, const float* xr, int64
 
 }  // namespace
 
+// edge_weight: CSR edge order (permuted + rounded here) unless TCGNN_W_TILE_ORDER says it already is the plan's
+// tile-ordered, tf32-rounded array (what the fused AGNN entry's SDDMM leaves behind).
 int spmm_launch(tcgnn_plan* plan, const float* x, int64_t ldx, const float* edge_weight, float* y, int64_t ldy,
-                int32_t dim, uint32_t op_flags, cudaStream_t stream) {
+                int32_t dim, uint32_t op_flags, cudaStream_t stream, int row_chunk) {
+  PlanView pv = plan->view();
+  if (row_chunk >= 0) {
+    if (row_chunk + 1 >= static_cast<int>(plan->row_chunk_win.size()) || plan->chunk_slice_ptr == nullptr) {
+      set_last_error("spmm: row chunk %d does not exist", row_chunk);
+      return TCGNN_ERR_INVALID_ARG;
+    }
+    pv.slice_ptr = plan->chunk_slice_ptr + static_cast<size_t>(row_chunk) * (plan->grid + 1);
+  }
   const float* wperm = nullptr;
   if (edge_weight != nullptr && plan->num_pairs > 0) {
-    int st = plan_ensure_eperm(plan, stream);
-    if (st != TCGNN_OK) return st;
-    st = plan_ensure_scratch(plan, &plan->weight_perm, static_cast<size_t>(plan->num_pairs));
-    if (st != TCGNN_OK) return st;
-    int g = (plan->num_pairs + 255) / 256;
-    if (g > 148 * 16) g = 148 * 16;
-    permute_weights_kernel<<<g, 256, 0, stream>>>(plan->eperm, edge_weight, plan->weight_perm, plan->num_pairs);
-    count_launch();
-    wperm = plan->weight_perm;
+    if (op_flags & TCGNN_W_TILE_ORDER) {
+      wperm = edge_weight;
+    } else {
+      int st = plan_ensure_eperm(plan, stream);
+      if (st != TCGNN_OK) return st;
+      st = plan_ensure_scratch(plan, &plan->weight_perm, static_cast<size_t>(plan->num_pairs));
+      if (st != TCGNN_OK) return st;
+      int g = (plan->num_pairs + 255) / 256;
+      if (g > 148 * 16) g = 148 * 16;
+      permute_weights_kernel<<<g, 256, 0, stream>>>(plan->eperm, edge_weight, plan->weight_perm, plan->num_pairs);
+      count_launch();
+      wperm = plan->weight_perm;
+    }
   }
   // Xr = tf32_rna(X), packed [num_cols, ldr] with ldr % 4 == 0 (16-byte aligned rows)
   int64_t ldr = (static_cast<int64_t>(dim) + 3) / 4 * 4;
   const float* xr = nullptr;
-  if ((op_flags & TCGNN_X_IS_TF32) && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (ldx & 3) == 0) {
+  if (x_is_prerounded(x, ldx, dim, op_flags)) {
     xr = x;      // the caller rounded X already (tcgnn_round_tf32) and its rows are 16-byte aligned
     ldr = ldx;
   } else {
@@ -657,10 +698,11 @@ int spmm_launch(tcgnn_plan* plan, const float* x, int64_t ldx, const float* edge
   }
   // one persistent CTA per SM, each owning a slice of the tile stream (plan->slice_ptr)
   const int grid = plan->grid;
+  const uint32_t mode = (op_flags & TCGNN_ACCUMULATE) ? kFlagAccumulate : 0u;
   for (int32_t f0 = 0; f0 < dim; f0 += 256) {
     const int32_t d = dim - f0 < 256 ? dim - f0 : 256;
-    cudaError_t e = d > 128 ? launch_pass<2>(plan, grid, xr + f0, ldr, wperm, y + f0, ldy, d, stream)
-                            : launch_pass<1>(plan, grid, xr + f0, ldr, wperm, y + f0, ldy, d, stream);
+    cudaError_t e = d > 128 ? launch_pass<2>(plan, pv, grid, xr + f0, ldr, wperm, y + f0, ldy, d, mode, stream)
+                            : launch_pass<1>(plan, pv, grid, xr + f0, ldr, wperm, y + f0, ldy, d, mode, stream);
     if (e != cudaSuccess) {
       set_last_error("spmm kernel launch failed: %s", cudaGetErrorString(e));
       return TCGNN_ERR_CUDA;

@@ -4,8 +4,16 @@ AGNNConv, gen_test_tensor, n_heads) with identical call signatures and identical
 main_tcgnn.py-style callers run unchanged.  The aggregation itself is the sm_100a library behind
 `import TCGNN`; there is no fallback -- importing this module without the built extension fails.
 
-Like the reference, every backward pass re-uses the forward kernel on the same CSR, i.e. it assumes
-a symmetric adjacency (reference gnn_conv.py:76-85).
+Like the reference, every backward pass by default re-uses the forward kernel on the same CSR, i.e. it
+assumes a symmetric adjacency (reference gnn_conv.py:76-85).  `set_assume_symmetric(False)` switches the
+backward passes to the transposed graph (`TCGNN.backward_T`: A^T, its SGT and its plan are derived on the
+device once per graph), which is what dX = A^T dY needs on a directed graph.
+
+The AGNN layer runs the fused edge pipeline (`TCGNN.forward_AGNN_fused` -> tcgnn_agnn_f32): SDDMM, the
+multiplication with attention_w and the weighted SpMM in one call, attention kept in the plan's tile order
+between the two kernels and for the backward pass; `set_fused_agnn(False)` restores the reference's
+three-call sequence (forward_ef -> torch.mm -> forward_AGNN, gnn_conv.py:125-132).  Both give bit-identical
+results.
 """
 from __future__ import annotations
 
@@ -18,6 +26,20 @@ import TCGNN
 
 n_heads = 1
 n_output = 8
+
+_assume_symmetric = True
+_fused_agnn = True
+
+
+def set_assume_symmetric(flag: bool) -> None:
+    """True (default, the reference's behaviour): backward aggregates over the forward CSR.  False: over A^T."""
+    global _assume_symmetric
+    _assume_symmetric = bool(flag)
+
+
+def set_fused_agnn(flag: bool) -> None:
+    global _fused_agnn
+    _fused_agnn = bool(flag)
 
 
 def gen_test_tensor(X_prime):
@@ -35,6 +57,13 @@ def _aggregate_weighted(X, graph, edge_attentions):
     return TCGNN.forward_AGNN(X.contiguous(), rp, ci, edge_attentions, bp, e2c, e2r)[0]
 
 
+def _aggregate_backward(dY, graph):
+    """dX of Y = A X: A^T dY; with a symmetric adjacency (the reference's assumption) that is A dY."""
+    if _assume_symmetric:
+        return TCGNN.backward(dY.contiguous(), *graph)[0]
+    return TCGNN.backward_T(dY.contiguous(), *graph)[0]
+
+
 class TCGNNFunction_SAG(torch.autograd.Function):
     """Plain scatter-and-gather: Y = A X (reference gnn_conv.py:26-49)."""
 
@@ -45,7 +74,7 @@ class TCGNNFunction_SAG(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, d_output):
-        return _aggregate(d_output, ctx.saved_tensors), None, None, None, None, None
+        return _aggregate_backward(d_output, ctx.saved_tensors), None, None, None, None, None
 
 
 class TCGNNFunction(torch.autograd.Function):
@@ -59,7 +88,7 @@ class TCGNNFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, d_output):
         X, weights, *graph = ctx.saved_tensors
-        d_input_prime = _aggregate(d_output, graph)
+        d_input_prime = _aggregate_backward(d_output, graph)
         d_input = torch.mm(d_input_prime, weights.t())
         d_weights = torch.mm(X.t(), d_input_prime)
         return d_input, d_weights, None, None, None, None, None
@@ -79,7 +108,7 @@ class TCGNNFunction_GIN(torch.autograd.Function):
         X_prime, weights, *graph = ctx.saved_tensors
         d_X_prime = torch.mm(d_output, weights.t())
         d_weights = torch.mm(X_prime.t(), d_output)
-        return _aggregate(d_X_prime, graph), d_weights, None, None, None, None, None
+        return _aggregate_backward(d_X_prime, graph), d_weights, None, None, None, None, None
 
 
 class TCGNNFunction_AGNN(torch.autograd.Function):
@@ -90,24 +119,38 @@ class TCGNNFunction_AGNN(torch.autograd.Function):
     def forward(ctx, X, weights, attention_w, row_pointers, column_index, blockPartition, edgeToColumn, edgeToRow):
         graph = (row_pointers, column_index, blockPartition, edgeToColumn, edgeToRow)
         X_prime = torch.mm(X, weights)
-        edge_feature = TCGNN.forward_ef(X_prime, *graph)[0]
-        edge_attentions = torch.mm(edge_feature.unsqueeze(-1), attention_w).transpose(0, 1).contiguous()  # [n_heads, E]
-        out = _aggregate_weighted(X_prime, graph, edge_attentions)
-        ctx.save_for_backward(X, weights, row_pointers, column_index, edge_attentions, blockPartition, edgeToColumn,
+        ctx.fused = _fused_agnn and _assume_symmetric
+        if ctx.fused:
+            # one call; the attention stays in the plan's tile order (no [E] round trip, no permutation passes)
+            out, attention, _ = TCGNN.forward_AGNN_fused(X_prime, row_pointers, column_index, attention_w.detach(),
+                                                         blockPartition, edgeToColumn, edgeToRow, False)
+        else:
+            edge_feature = TCGNN.forward_ef(X_prime, *graph)[0]
+            attention = torch.mm(edge_feature.unsqueeze(-1), attention_w).transpose(0, 1).contiguous()  # [n_heads, E]
+            out = _aggregate_weighted(X_prime, graph, attention)
+        ctx.save_for_backward(X, weights, row_pointers, column_index, attention, blockPartition, edgeToColumn,
                               edgeToRow)
         return out
 
     @staticmethod
     def backward(ctx, d_output):
-        X, weights, row_pointers, column_index, edge_attentions, blockPartition, edgeToColumn, edgeToRow = \
+        X, weights, row_pointers, column_index, attention, blockPartition, edgeToColumn, edgeToRow = \
             ctx.saved_tensors
         graph = (row_pointers, column_index, blockPartition, edgeToColumn, edgeToRow)
-        d_input_prime = _aggregate_weighted(d_output, graph, edge_attentions)
+        d_output = d_output.contiguous()
+        if ctx.fused:
+            d_input_prime = TCGNN.forward_AGNN_tile(d_output, row_pointers, column_index, attention, blockPartition,
+                                                    edgeToColumn, edgeToRow)[0]
+        elif _assume_symmetric:
+            d_input_prime = _aggregate_weighted(d_output, graph, attention)
+        else:
+            d_input_prime = TCGNN.backward_T_AGNN(d_output, row_pointers, column_index, attention, blockPartition,
+                                                  edgeToColumn, edgeToRow)[0]
         d_input = torch.mm(d_input_prime, weights.t())
         d_weights = torch.mm(X.t(), d_input_prime)
         # the reference's attention "gradient" (gnn_conv.py:150-155): SDDMM of d_output contracted with the
         # column ids -- kept as is, it only has to have the parameter's shape [1, n_heads]
-        d_attention = TCGNN.forward_ef(d_output.contiguous(), *graph)[0]
+        d_attention = TCGNN.forward_ef(d_output, *graph)[0]
         d_attention_w = torch.mm(d_attention[None, :].expand(n_heads, -1), column_index[:, None].float()).t()
         return d_input, d_weights, d_attention_w, None, None, None, None, None
 

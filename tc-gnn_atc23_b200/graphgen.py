@@ -91,9 +91,33 @@ def synthetic_graph(num_nodes: int, target_nnz: int, kind: str = "rmat", seed: i
             k = torch.cat([k, dst * num_nodes + src])
         keys = torch.unique(torch.cat([keys, k]))
         del src, dst, k
-    if keys.numel() > target_nnz:   # mirrored self-loops can overshoot by a handful; drop from the tail
-        keys = keys[:target_nnz]
+    if keys.numel() > target_nnz:
+        keys = _trim(keys, num_nodes, target_nnz, symmetric)
     return csr_from_keys(keys, num_nodes)
+
+
+def _trim(keys: torch.Tensor, num_nodes: int, target_nnz: int, symmetric: bool) -> torch.Tensor:
+    """Drop the overshoot from the tail.  On a symmetric graph an off-diagonal pair leaves together with its mirror
+    (cutting `keys[:target]` would keep (a, b) without (b, a)); the result may be one entry short of the target."""
+    excess = keys.numel() - target_nnz
+    if not symmetric:
+        return keys[:target_nnz]
+    rows = torch.div(keys, num_nodes, rounding_mode="floor")
+    cols = keys - rows * num_nodes
+    lower = torch.nonzero(rows > cols).flatten()          # one representative per mirrored pair, sorted by key
+    n_pairs = min((excess + 1) // 2, lower.numel())
+    drop = lower[lower.numel() - n_pairs:]
+    keep = torch.ones(keys.numel(), dtype=torch.bool, device=keys.device)
+    keep[drop] = False
+    mirror = cols[drop] * num_nodes + rows[drop]
+    keep[torch.searchsorted(keys, mirror)] = False
+    keys = keys[keep]
+    if keys.numel() > target_nnz:                         # only self-loops were left to drop
+        diag = torch.nonzero(torch.div(keys, num_nodes, rounding_mode="floor") == keys % num_nodes).flatten()
+        keep = torch.ones(keys.numel(), dtype=torch.bool, device=keys.device)
+        keep[diag[diag.numel() - min(diag.numel(), keys.numel() - target_nnz):]] = False
+        keys = keys[keep]
+    return keys
 
 
 def workload(name: str, device="cuda", seed: int = 0):

@@ -9,10 +9,16 @@ New work -- the reference is single process / single GPU.  Design
   * boundaries are chosen on the prefix sum of the CSR row pointer so the stored non-zeros (= the
     gather work) per rank are balanced, not the row counts (R-MAT rows are heavily skewed);
   * column ids stay global.  Per layer the only exchange is ONE all-gather of the layer input
-    (every rank contributes its panel of X, receives the others') over NCCL / NVLink; the output of
+    (every rank contributes its panel of X, receives the others') over NVLink; the output of
     SpMM stays sharded -- it is the rank's panel of the next layer's input;
-  * the kernels take the gathered matrix plus the panel plan (`tcgnn_plan_create_panel`), AGNN's
-    SDDMM + weighted SpMM share one gather.
+  * GCN/GIN/SAG aggregation (`aggregate`) overlaps that exchange with the kernels: the panel's sub-graph
+    is split once by SOURCE panel, Y = sum_p A[panel, cols of p] . X[p]; the own-panel product starts
+    at once, every other product as soon as that source's rows have landed (copy-engine pushes into
+    symmetric memory + a flag, a stream-ordered wait in front of each launch, TCGNN_ACCUMULATE).  A
+    source ships only the rows the destination's panel references when that is a small part of its
+    panel (packed, column ids remapped) -- the R-MAT 10 M graph references ~1/3 of the rows;
+  * AGNN's SDDMM + weighted SpMM take the gathered matrix plus the panel plan
+    (`tcgnn_plan_create_panel`) and share one gather.
 
 Host-side logic here is device-agnostic (the world_size-2 gloo tests run it on CPU); the compute
 calls go to the `TCGNN` extension and need a GPU -- there is no CPU fallback.
@@ -30,7 +36,8 @@ from config import BLK_H, BLK_W
 
 
 def partition_rows(row_ptr: torch.Tensor, world_size: int, blk_h: int = BLK_H,
-                   block_partition: Optional[torch.Tensor] = None, window_cost: int = 3) -> List[int]:
+                   block_partition: Optional[torch.Tensor] = None, window_cost: int = 3,
+                   send_cost_per_row: float = 0.0) -> List[int]:
     """Row boundaries [b_0 = 0, ..., b_world = N], each a multiple of `blk_h` (except N).  Deterministic,
     identical on every rank.
 
@@ -45,6 +52,8 @@ def partition_rows(row_ptr: torch.Tensor, world_size: int, blk_h: int = BLK_H,
     last = n // blk_h * blk_h if n >= blk_h else 0
     if block_partition is not None:
         cost = torch.clamp(block_partition.to(torch.int64).cpu(), min=1) + int(window_cost)
+        if send_cost_per_row > 0 and world_size > 1:
+            return _partition_minmax(cost.numpy(), float(send_cost_per_row) * blk_h, world_size, n, blk_h)
         pre = torch.cumsum(cost, 0)                      # cost of windows [0, w]
         total = int(pre[-1]) if pre.numel() else 0
         bounds = [0]
@@ -67,6 +76,61 @@ def partition_rows(row_ptr: torch.Tensor, world_size: int, blk_h: int = BLK_H,
         bounds.append(r)
     bounds.append(n)
     return bounds
+
+
+def _partition_minmax(compute, send_per_window: float, world: int, n: int, blk_h: int) -> List[int]:
+    """Window cuts minimising max over panels of max(sum compute, sum send): bisection on the bound T, greedy
+    feasibility (extend a panel while both sums stay <= T)."""
+    import numpy as np
+    nwin = len(compute)
+    pre_c = np.concatenate([[0.0], np.cumsum(compute, dtype=np.float64)])
+
+    def cuts(t):
+        out, w = [0], 0
+        for _ in range(world):
+            # furthest end with compute <= t and send <= t
+            hi_c = int(np.searchsorted(pre_c, pre_c[w] + t, side="right")) - 1
+            hi_s = w + int(t // send_per_window) if send_per_window > 0 else nwin
+            e = max(min(hi_c, hi_s, nwin), w)
+            out.append(e)
+            w = e
+        return out
+
+    lo = max(pre_c[-1] / world, send_per_window * nwin / world, float(np.max(compute)) if nwin else 0.0, send_per_window)
+    hi = max(pre_c[-1], send_per_window * nwin) + 1.0
+    for _ in range(60):
+        mid = 0.5 * (lo + hi)
+        if cuts(mid)[-1] >= nwin:
+            hi = mid
+        else:
+            lo = mid
+    c = cuts(hi)
+    c[-1] = nwin
+    bounds = [min(w * blk_h, n) for w in c]
+    bounds[-1] = n
+    last = n // blk_h * blk_h if n >= blk_h else 0
+    return [0] + [min(b, last) for b in bounds[1:-1]] + [n]
+
+
+def default_send_cost(world_size: int) -> float:
+    """Send cost of one feature row in TC-block units: a row of D floats goes to world - 1 peers over NVLink
+    (~0.6 TB/s out of a GPU) while a TC block gathers 8 such rows through L2 at ~10 TB/s -- D cancels."""
+    v = os.environ.get("TCGNN_SEND_COST")
+    if v is not None:
+        return float(v)
+    return (world_size - 1) / 8.0 * 14.0 if world_size > 2 else 0.0
+
+
+def _all_ranks_ok(ok: bool, device, group) -> bool:
+    """Collective AND of a per-rank success flag (decides fused-versus-fallback identically on every rank)."""
+    t = torch.tensor([1 if ok else 0], dtype=torch.int32, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
+    return bool(int(t.item()) == 1)
+
+
+class OverlapState:
+    """Buffers of the overlapped exchange for one feature width (see RowPanel.aggregate_overlapped)."""
+    EPOCH_RING = 1 << 20   # flag values are read from a device-resident ramp by the copy engine
 
 
 class RowPanel:
@@ -92,7 +156,8 @@ class RowPanel:
         if bounds is not None:
             self.bounds = list(bounds)
         else:
-            self.bounds = partition_rows(row_ptr, world_size, block_partition=sgt[0] if sgt is not None else None)
+            self.bounds = partition_rows(row_ptr, world_size, block_partition=sgt[0] if sgt is not None else None,
+                                         send_cost_per_row=default_send_cost(world_size) if sgt is not None else 0.0)
         if len(self.bounds) != world_size + 1 or self.bounds[0] != 0 or self.bounds[-1] != self.num_cols:
             raise ValueError("bounds must be [0, ..., num_nodes] with world_size + 1 entries")
         for b in self.bounds[1:-1]:
@@ -126,6 +191,9 @@ class RowPanel:
         self._x_all = None
         self._symm = {}    # feature width -> (symmetric buffer, handle, peer views, multicast?)
         self._symm_unavailable = False
+        self._sub = None   # per-source-panel sub-graphs (overlapped exchange)
+        self._ovl = {}     # feature width -> OverlapState
+        self._ovl_unavailable = False
 
     # ------------------------------------------------------------------ exchange
     @property
@@ -154,18 +222,28 @@ class RowPanel:
             raise ValueError(f"x_local has {x_local.shape[0]} rows, the panel has {self.num_rows}")
         d = x_local.shape[1]
         mode = os.environ.get("TCGNN_EXCHANGE", "auto")
+        if mode in ("overlap",):
+            mode = "auto"          # the overlapped path is `aggregate`; a plain gather uses the fused exchange
         if (round_tf32 and out is None and self.world_size > 1 and x_local.is_cuda and d % 4 == 0
                 and mode != "nccl" and not self._symm_unavailable and dist.get_backend(group) == "nccl"):
-            try:
+            # Setup (symmetric allocation + rendezvous) can fail on one rank only (out of memory, no P2P access):
+            # the ranks agree on fused-versus-NCCL collectively, once per feature width, BEFORE any barrier or data
+            # movement.  After that nothing is caught: an error inside the exchange is a real error on every rank.
+            if d not in self._symm:
+                err = None
+                try:
+                    self._setup_fused(x_local, group, mode)
+                except (RuntimeError, ImportError, AttributeError) as exc:
+                    err = exc
+                if not _all_ranks_ok(err is None, x_local.device, group):
+                    self._symm.pop(d, None)
+                    if mode != "auto":
+                        raise RuntimeError(f"TCGNN_EXCHANGE={mode}: fused exchange unavailable on some rank ({err})")
+                    self._symm_unavailable = True
+                    print(f"[tcgnn sharding] rank {self.rank}: fused exchange unavailable ({err}); every rank uses "
+                          f"the NCCL all-gather", file=sys.stderr, flush=True)
+            if not self._symm_unavailable:
                 return self._fused_exchange(x_local.contiguous(), group, mode)
-            except (RuntimeError, ImportError, AttributeError) as exc:
-                # symmetric memory needs P2P access + a working rendezvous on every rank; the failure is collective
-                # (same platform everywhere), so every rank falls back to the NCCL all-gather together
-                if mode != "auto":
-                    raise
-                self._symm_unavailable = True
-                print(f"[tcgnn sharding] rank {self.rank}: fused exchange unavailable ({exc}); using NCCL all-gather",
-                      file=sys.stderr, flush=True)
         if round_tf32 and self.num_rows > 0:
             import TCGNN
             x_local = TCGNN.round_tf32(x_local.contiguous())
@@ -189,22 +267,23 @@ class RowPanel:
                                    group=group)
         return out
 
-    def _fused_exchange(self, x_local: torch.Tensor, group, mode: str) -> torch.Tensor:
-        import TCGNN
+    def _setup_fused(self, x_local: torch.Tensor, group, mode: str) -> None:
         import torch.distributed._symmetric_memory as symm_mem
         d = x_local.shape[1]
-        st = self._symm.get(d)
-        if st is None:
-            grp = group if group is not None else dist.group.WORLD
-            buf = symm_mem.empty((self.num_cols, d), dtype=torch.float32, device=x_local.device)
-            hdl = symm_mem.rendezvous(buf, grp)
-            peers = [hdl.get_buffer(p, (self.num_cols, d), torch.float32) for p in range(self.world_size)]
-            use_mc = mode in ("auto", "multicast") and bool(getattr(hdl, "has_multicast_support", False)) \
-                and int(hdl.multicast_ptr) != 0
-            if mode == "multicast" and not use_mc:
-                raise RuntimeError("TCGNN_EXCHANGE=multicast but the group has no NVSwitch multicast support")
-            st = self._symm[d] = (buf, hdl, peers, use_mc)
-        buf, hdl, peers, use_mc = st
+        grp = group if group is not None else dist.group.WORLD
+        buf = symm_mem.empty((self.num_cols, d), dtype=torch.float32, device=x_local.device)
+        hdl = symm_mem.rendezvous(buf, grp)
+        peers = [hdl.get_buffer(p, (self.num_cols, d), torch.float32) for p in range(self.world_size)]
+        use_mc = mode in ("auto", "multicast") and bool(getattr(hdl, "has_multicast_support", False)) \
+            and int(hdl.multicast_ptr) != 0
+        if mode == "multicast" and not use_mc:
+            raise RuntimeError("TCGNN_EXCHANGE=multicast but the group has no NVSwitch multicast support")
+        self._symm[d] = (buf, hdl, peers, use_mc)
+
+    def _fused_exchange(self, x_local: torch.Tensor, group, mode: str) -> torch.Tensor:
+        import TCGNN
+        d = x_local.shape[1]
+        buf, hdl, peers, use_mc = self._symm[d]
         row_bytes = d * 4
         w, me = self.world_size, self.rank
         hdl.barrier(channel=0)                 # every rank has finished reading the previous gathered matrix
@@ -270,9 +349,189 @@ class RowPanel:
         return x_local.is_cuda and x_local.shape[1] % 4 == 0
 
     def aggregate(self, x_local: torch.Tensor, group=None) -> torch.Tensor:
-        """GCN/GIN/SAG aggregation of one layer: all-gather + panel SpMM -> the panel of A.X."""
+        """GCN/GIN/SAG aggregation of one layer -> the panel of A.X.  On NCCL groups (TCGNN_EXCHANGE=auto|overlap)
+        the exchange is overlapped with the kernels source panel by source panel (`aggregate_overlapped`); else
+        all-gather + one panel SpMM."""
+        mode = os.environ.get("TCGNN_EXCHANGE", "auto")
         pre = self._can_preround(x_local)
+        if (pre and mode in ("auto", "overlap") and self.world_size > 1 and not self._ovl_unavailable
+                and dist.get_backend(group) == "nccl"):
+            d = x_local.shape[1]
+            if d not in self._ovl:
+                err = None
+                try:
+                    self._setup_overlap(d, x_local.device, group)
+                except (RuntimeError, ImportError, AttributeError) as exc:
+                    err = exc
+                if not _all_ranks_ok(err is None, x_local.device, group):
+                    self._ovl.pop(d, None)
+                    if mode == "overlap":
+                        raise RuntimeError(f"TCGNN_EXCHANGE=overlap unavailable on some rank ({err})")
+                    self._ovl_unavailable = True
+                    print(f"[tcgnn sharding] rank {self.rank}: overlapped exchange unavailable ({err}); every rank "
+                          f"gathers first", file=sys.stderr, flush=True)
+            if not self._ovl_unavailable:
+                return self.aggregate_overlapped(x_local)
         return self.spmm(self.all_gather(x_local, group, round_tf32=pre), x_is_tf32=pre)
+
+    # ------------------------------------------------------------------ overlapped exchange (GCN path)
+    def build_source_subgraphs(self, dense_fraction: float = 0.7):
+        """Split the panel's graph by SOURCE panel p: the edges whose column lies in panel p, as a CSR over the
+        panel's rows whose column ids index the rows that will be shipped -- all of panel p (`dense`: ids rebased to
+        the panel) or only the sorted unique referenced rows `ref` (ids = rank in `ref`).  Pure tensor code (runs on
+        the CPU in the gloo tests); the SGT of every sub-graph comes from TCGNN.preprocess_panel."""
+        if self._sub is not None:
+            return self._sub
+        import TCGNN
+        ci = self.column_index.long()
+        e2r = self.edgeToRow.long()
+        dev = ci.device
+        subs = []
+        for p in range(self.world_size):
+            b0, b1 = self.bounds[p], self.bounds[p + 1]
+            mask = (ci >= b0) & (ci < b1)
+            cols = ci[mask]
+            counts = torch.bincount(e2r[mask], minlength=self.num_rows)
+            rp = torch.zeros(self.num_rows + 1, dtype=torch.int64, device=dev)
+            torch.cumsum(counts, 0, out=rp[1:])
+            ref = torch.unique(cols)                                   # sorted global ids
+            dense = p == self.rank or ref.numel() >= dense_fraction * max(b1 - b0, 1)
+            if dense:
+                local = cols - b0
+                n_src = b1 - b0
+                ref_rows = None
+            else:
+                local = torch.searchsorted(ref, cols)
+                n_src = int(ref.numel())
+                ref_rows = (ref - b0).to(torch.int32)                  # rows of panel p, relative to its first row
+            rp32 = rp.to(torch.int32).contiguous()
+            ci32 = local.to(torch.int32).contiguous()
+            nwin = (self.num_rows + BLK_H - 1) // BLK_H
+            bp = torch.zeros(nwin, dtype=torch.int32, device=dev)
+            e2c = torch.zeros(max(ci32.numel(), 1), dtype=torch.int32, device=dev)[:ci32.numel()]
+            e2r_s = torch.zeros(max(ci32.numel(), 1), dtype=torch.int32, device=dev)[:ci32.numel()]
+            if self.num_rows > 0:
+                TCGNN.preprocess_panel(ci32, rp32, self.num_rows, max(n_src, 1), BLK_H, BLK_W, bp, e2c, e2r_s)
+            subs.append({"graph": (rp32, ci32, bp, e2c, e2r_s), "n_src": n_src, "ref_rows": ref_rows,
+                         "dense": dense, "edges": int(ci32.numel())})
+        self._sub = subs
+        return subs
+
+    def _setup_overlap(self, d: int, device, group) -> None:
+        import torch.distributed._symmetric_memory as symm_mem
+        w, me = self.world_size, self.rank
+        grp = group if group is not None else dist.group.WORLD
+        subs = self.build_source_subgraphs()
+        # need[q][p] = rows rank q wants from rank p (0 on the diagonal); every rank learns the whole matrix
+        mine = torch.tensor([0 if p == me else subs[p]["n_src"] for p in range(w)], dtype=torch.int64, device=device)
+        need = [torch.zeros(w, dtype=torch.int64, device=device) for _ in range(w)]
+        dist.all_gather(need, mine, group=group)
+        need = torch.stack(need).cpu()
+        # the row lists go to their sources (empty = "your whole panel")
+        send = [torch.zeros(0, dtype=torch.int32, device=device) if (p == me or subs[p]["dense"])
+                else subs[p]["ref_rows"].to(device) for p in range(w)]
+        cnt_out = torch.tensor([t.numel() for t in send], dtype=torch.int64, device=device)
+        cnt_in = torch.zeros(w, dtype=torch.int64, device=device)
+        dist.all_to_all_single(cnt_in, cnt_out, group=group)
+        cnt_in_l = [int(v) for v in cnt_in.cpu()]
+        recv = torch.zeros(max(sum(cnt_in_l), 1), dtype=torch.int32, device=device)[:sum(cnt_in_l)]
+        dist.all_to_all_single(recv, torch.cat(send) if w else recv, output_split_sizes=cnt_in_l,
+                               input_split_sizes=[int(v) for v in cnt_out.cpu()], group=group)
+        lists = list(torch.split(recv, cnt_in_l))           # lists[q] = my rows rank q wants (empty: all of them)
+        # receive area: the sources' rows back to back in rank order; two copies (step parity) so a fast peer's
+        # next push never lands in the rows a slow rank is still reading
+        offs = torch.zeros(w, w + 1, dtype=torch.int64)
+        offs[:, 1:] = torch.cumsum(need, 1)
+        rows_max = int(offs[:, -1].max())
+        st = OverlapState()
+        st.need, st.offs = need, offs
+        st.recv = symm_mem.empty((2, max(rows_max, 1), d), dtype=torch.float32, device=device)
+        st.recv_hdl = symm_mem.rendezvous(st.recv, grp)
+        st.flags = symm_mem.empty((w,), dtype=torch.int32, device=device)
+        st.flags.zero_()
+        st.flags_hdl = symm_mem.rendezvous(st.flags, grp)
+        st.peer_recv = [st.recv_hdl.get_buffer(q, (2, max(rows_max, 1), d), torch.float32) for q in range(w)]
+        st.peer_flags = [st.flags_hdl.get_buffer(q, (w,), torch.int32) for q in range(w)]
+        st.lists = lists
+        st.stage = [torch.empty((int(need[q, me]), d), dtype=torch.float32, device=device)
+                    if (q != me and lists[q].numel() > 0) else None for q in range(w)]
+        st.xr = [torch.empty((self.num_rows, d), dtype=torch.float32, device=device) for _ in range(2)]
+        st.vals = torch.arange(OverlapState.EPOCH_RING, dtype=torch.int32, device=device)
+        st.err = torch.zeros(1, dtype=torch.int32, device=device)
+        st.copy_stream = torch.cuda.Stream(device=device)
+        st.ev_round = [torch.cuda.Event() for _ in range(2)]
+        st.epoch = 0
+        torch.cuda.synchronize(device)
+        st.flags_hdl.barrier(channel=0)                    # flags are zeroed everywhere before anybody pushes
+        self._ovl[d] = st
+
+    def aggregate_overlapped(self, x_local: torch.Tensor) -> torch.Tensor:
+        """One layer's aggregation with the exchange hidden behind the kernels.
+
+        This rank rounds its panel once, then its copy engines push the panel (or the packed rows a destination
+        references) into every peer's receive area, nearest rank first, each push followed by a 4-byte flag write;
+        meanwhile its SMs compute the own-panel product, then -- in the order the pushes of the other ranks arrive
+        -- one TCGNN_ACCUMULATE product per source panel, each behind a stream-ordered wait on that source's flag.
+        No barrier: the receive area is double-buffered by step parity, and a rank's pushes of step k + 1 are
+        ordered after its own kernels of step k, which needed everybody's data of step k."""
+        import TCGNN
+        d = x_local.shape[1]
+        st = self._ovl[d]
+        subs = self._sub
+        w, me = self.world_size, self.rank
+        st.epoch += 1
+        if st.epoch >= OverlapState.EPOCH_RING - 1:
+            raise RuntimeError("overlapped exchange: step counter exhausted; call reset_overlap()")
+        epoch, b = st.epoch, st.epoch & 1
+        cur = torch.cuda.current_stream(x_local.device)
+        xr = st.xr[b]
+        if self.num_rows > 0:
+            TCGNN.round_tf32_into(x_local.contiguous(), xr.data_ptr(), d, False)
+        st.ev_round[b].record(cur)
+        with torch.cuda.stream(st.copy_stream):
+            st.copy_stream.wait_event(st.ev_round[b])
+            for k in range(1, w):
+                q = (me + k) % w
+                n = int(st.need[q, me])
+                if n > 0:
+                    if st.lists[q].numel() > 0:
+                        TCGNN.gather_rows(xr, st.lists[q], st.stage[q])
+                        src = st.stage[q]
+                    else:
+                        src = xr
+                    o = int(st.offs[q, me])
+                    st.peer_recv[q][b, o:o + n].copy_(src, non_blocking=True)
+                st.peer_flags[q][me:me + 1].copy_(st.vals[epoch:epoch + 1], non_blocking=True)
+        if self.num_rows == 0:
+            return x_local.new_zeros((0, d))
+        y = TCGNN.source_forward(xr, *subs[me]["graph"], x_is_tf32=True)[0]
+        timeout_ms = int(os.environ.get("TCGNN_FLAG_TIMEOUT_MS", "20000"))
+        for k in range(1, w):
+            p = (me - k) % w
+            TCGNN.stream_wait_flag(st.flags, p, epoch, timeout_ms, st.err)
+            n = int(st.need[me, p])
+            if n > 0 and subs[p]["edges"] > 0:
+                o = int(st.offs[me, p])
+                TCGNN.source_forward(st.recv[b, o:o + n], *subs[p]["graph"], x_is_tf32=True, accumulate_into=y)
+        return y
+
+    def overlap_check(self) -> None:
+        """Raises if a flag wait of the overlapped exchange timed out (synchronises; call outside timed regions)."""
+        for st in self._ovl.values():
+            if int(st.err.item()) != 0:
+                raise RuntimeError("overlapped exchange: a source panel's rows did not arrive within "
+                                   "TCGNN_FLAG_TIMEOUT_MS; the result of that step is incomplete")
+
+    def overlap_stats(self, d: int):
+        """Rows / bytes this rank receives per step in the overlapped exchange vs a full all-gather."""
+        st = self._ovl.get(d)
+        if st is None:
+            return None
+        rows = int(st.need[self.rank].sum())
+        full = self.num_cols - self.num_rows
+        return {"recv_rows": rows, "full_gather_rows": full, "recv_bytes": rows * d * 4,
+                "dense_sources": sum(1 for p, sb in enumerate(self._sub) if p != self.rank and sb["dense"]),
+                "packed_sources": sum(1 for p, sb in enumerate(self._sub) if p != self.rank and not sb["dense"])}
 
     def agnn_aggregate(self, x_local: torch.Tensor, attention_w: torch.Tensor, group=None):
         """AGNN aggregation (reference gnn_conv.py:125-132) on the panel: one gather serves SDDMM and

@@ -54,6 +54,15 @@ def lib() -> C.CDLL:
         L.tcgnn_push_rows.argtypes = [vp, vp, i32, vp, vp, i32, i64, vp]
         L.tcgnn_push_rows.restype = C.c_int
         L.tcgnn_round_tf32_multicast.argtypes = [vp, i64, vp, i64, i64, i32, vp]
+        L.tcgnn_agnn_f32.argtypes = [vp, vp, i64, vp, vp, i64, vp, vp, i32, u32, vp]
+        L.tcgnn_csr_transpose.argtypes = [vp, vp, i32, i32, i64, vp, vp, vp, vp]
+        L.tcgnn_gather_rows.argtypes = [vp, i64, vp, i64, vp, vp]
+        L.tcgnn_stream_wait_flag.argtypes = [vp, i32, i32, vp, vp]
+        L.tcgnn_sddmm_f32_host.argtypes = [vp, vp, i64, vp, i32, vp]
+        L.tcgnn_agnn_f32_host.argtypes = [vp, vp, i64, vp, vp, i64, vp, i32, vp]
+        for name in ("tcgnn_agnn_f32", "tcgnn_csr_transpose", "tcgnn_gather_rows", "tcgnn_stream_wait_flag",
+                     "tcgnn_sddmm_f32_host", "tcgnn_agnn_f32_host"):
+            getattr(L, name).restype = C.c_int
         for name in ("tcgnn_spmm_f32_ex", "tcgnn_sddmm_f32_ex", "tcgnn_round_tf32", "tcgnn_round_tf32_multicast"):
             getattr(L, name).restype = C.c_int
         L.tcgnn_debug_umma_bench.argtypes = [u64, u64, u32, i32, i32, i32, i32, i32, i32, i32, i32, C.POINTER(i64), vp]
@@ -134,6 +143,20 @@ class Plan:
         check(lib().tcgnn_sddmm_f32(self._h, _ptr(x), x.stride(0), _ptr(out), dim, _stream()), "tcgnn_sddmm_f32")
         return out
 
+    def spmm_ex(self, x, y, edge_weight=None, flags=0, dim=None):
+        """tcgnn_spmm_f32_ex: flags = X_IS_TF32 | ACCUMULATE | W_TILE_ORDER."""
+        dim = x.shape[1] if dim is None else dim
+        check(lib().tcgnn_spmm_f32_ex(self._h, _ptr(x), x.stride(0), _ptr(edge_weight), _ptr(y), y.stride(0), dim,
+                                      flags, _stream()), "tcgnn_spmm_f32_ex")
+        return y
+
+    def agnn(self, x, attention_w, y, att_tile_out=None, edge_out=None, flags=0, dim=None):
+        """tcgnn_agnn_f32: fused SDDMM -> x attention_w -> weighted SpMM."""
+        dim = x.shape[1] if dim is None else dim
+        check(lib().tcgnn_agnn_f32(self._h, _ptr(x), x.stride(0), _ptr(attention_w), _ptr(y), y.stride(0),
+                                   _ptr(att_tile_out), _ptr(edge_out), dim, flags, _stream()), "tcgnn_agnn_f32")
+        return y
+
     def close(self):
         if self._h:
             lib().tcgnn_plan_destroy(self._h)
@@ -155,6 +178,23 @@ def debug_umma(a_image, b_image, adesc, bdesc, idesc, ksteps, a_step, b_step, nc
     check(lib().tcgnn_debug_umma(_ptr(a), a.size, _ptr(b), b.size, adesc, bdesc, idesc, ksteps, a_step, b_step,
                                  _ptr(out), ncols, _stream()), "tcgnn_debug_umma")
     return out
+
+
+X_IS_TF32, ACCUMULATE, W_TILE_ORDER = 1, 2, 4
+
+
+def csr_transpose(row_ptr, col_idx, num_cols=None):
+    """tcgnn_csr_transpose on device int32 tensors -> (row_ptr_t, col_idx_t, edge_map_t)."""
+    import torch
+    n = row_ptr.numel() - 1
+    m = n if num_cols is None else num_cols
+    e = col_idx.numel()
+    rp_t = torch.empty(m + 1, dtype=torch.int32, device=row_ptr.device)
+    ci_t = torch.empty(e, dtype=torch.int32, device=row_ptr.device)
+    map_t = torch.empty(e, dtype=torch.int32, device=row_ptr.device)
+    check(lib().tcgnn_csr_transpose(_ptr(row_ptr), _ptr(col_idx), n, m, e, _ptr(rp_t), _ptr(ci_t), _ptr(map_t),
+                                    _stream()), "tcgnn_csr_transpose")
+    return rp_t, ci_t, map_t
 
 
 def launch_count(reset=False) -> int:
