@@ -13,8 +13,14 @@ dataset is a download that is not available offline), generated on the GPU.
   value   device-timed throughput, inputs resident in HBM, L2 flushed between iterations
   e2e     same metric through the operator API with HOST feature buffers: pinned-host -> device copy
           of X, the operator, device -> pinned-host copy of the result, all inside the timed region
-  N > 1   strong scaling: the same graph split into destination-row panels (sharding.py), every step
-          = one NCCL all-gather of X + the panel kernels; max over ranks
+  N > 1   strong scaling: the same graph split into destination-row panels (sharding.py); every step = the
+          exchange of X over NVLink (copy-engine pushes into symmetric memory, overlapped with the kernels
+          source panel by source panel) + the panel kernels; max over ranks
+  parity  every line carries a bit-exact check of the timed path on integer features against torch's fp64
+          CSR product (each rank checks its panel; max over ranks)
+  variants  the default N = 1 line also measures the reddit-sized UNIFORM graph (tile density of the real
+          Reddit) next to the R-MAT default and the reference's kernels on it; N = 1 and N = 8 lines add the
+          R-MAT 10 M / 200 M, D = 256 configuration (BASELINE.json configs[4])
 
 `--impl reference` runs the UNMODIFIED reference extension (oracle/_ref, built from
 /root/reference/TCGNN_conv by oracle/build_ref.sh; sm_100 SASS of its wmma kernels) on the same
@@ -118,6 +124,32 @@ def ncu_traffic(kernel_key):
         with open(p) as fh:
             return json.load(fh).get(kernel_key)
     return None
+
+
+def measured_l2_gather_peak():
+    """L2 -> SM gather ceiling measured on this pool's B200 by tools/l2_gather_bench (random 512-byte row gathers
+    of an L2-resident matrix with the kernel's own LDGSTS access shape, no MMA): bytes per SM clock, whole chip."""
+    p = os.path.join(ROOT, "profiles", "l2_gather_peak.json")
+    if os.path.exists(p):
+        with open(p) as fh:
+            d = json.load(fh)
+        return float(d["bytes_per_clk"]), "measured (profiles/l2_gather_peak.json, tools/l2_gather_bench)"
+    return 6300.0, "B300_MICROARCH.md LTS cap ~6300 B/clk (not measured here)"
+
+
+def compulsory_bytes(op, n_rows, n_cols, n_edges, dim, tiles):
+    """Bytes that must cross the HBM interface at least once per launch: X once, the output once, the plan's tile
+    stream once (64 B per TC block), CSR-order edge outputs once."""
+    x_and_y = 4 * dim * (n_cols + n_rows)
+    if op == "spmm":
+        return x_and_y + 64 * tiles
+    if op == "sddmm":
+        return 4 * dim * n_cols + 64 * tiles + 8 * n_edges
+    return x_and_y + 2 * 64 * tiles + 8 * n_edges     # agnn: both kernels stream the tiles; tile-ordered attention out + in
+
+
+def workload_string(name, n, nnz, dim, op, seed, kind):
+    return f"{name}: N={n} nnz={nnz} D={dim} op={op} seed={seed} ({kind} graph, symmetric)"
 
 
 def algorithmic_bytes(op, n_rows, n_edges, dim):
@@ -232,6 +264,205 @@ def timed_steps(step, steps, warmup, flush, world, sampler=None, on_timed_start=
     return ms.cpu().numpy(), clocks
 
 
+def quiet_preprocess(TCGNN, ci, rp, n, bp, e2c, e2r):
+    devnull = os.open(os.devnull, os.O_WRONLY)   # TCGNN.preprocess printf()s TC_Blocks like the reference
+    saved = os.dup(1)
+    os.dup2(devnull, 1)
+    try:
+        TCGNN.preprocess_gpu(ci, rp, n, 16, 8, bp, e2c, e2r)
+    finally:
+        os.dup2(saved, 1)
+        os.close(saved)
+        os.close(devnull)
+
+
+class Workload:
+    """One graph + the step functions of one op on `world` GPUs (world == 1: the operators on the whole graph;
+    world > 1: this rank's row panel behind sharding.RowPanel)."""
+
+    def __init__(self, name, op, dim, seed, world, rank, dev):
+        import graphgen
+        import TCGNN
+        from sharding import RowPanel
+        self.TCGNN = TCGNN
+        self.name, self.op, self.world, self.rank, self.dev = name, op, world, rank, dev
+        n, target_nnz, wl_dim, kind = graphgen.WORKLOADS[name]
+        self.n, self.kind, self.seed = n, kind, seed
+        self.dim = dim or wl_dim
+        t0 = time.perf_counter()
+        self.rp, self.ci = graphgen.synthetic_graph(n, target_nnz, kind=kind, seed=seed, device=dev)
+        self.nnz = int(self.ci.numel())
+        torch.cuda.synchronize()
+        self.t_graph = time.perf_counter() - t0
+        x_full = graphgen.features(n, self.dim, seed=seed, device=dev)
+        t0 = time.perf_counter()
+        self.panel = None
+        if world == 1:
+            bp = torch.zeros((n + 15) // 16, dtype=torch.int32, device=dev)
+            e2c = torch.zeros(self.nnz, dtype=torch.int32, device=dev)
+            e2r = torch.zeros(self.nnz, dtype=torch.int32, device=dev)
+            quiet_preprocess(TCGNN, self.ci, self.rp, n, bp, e2c, e2r)
+            self.graph = (self.rp, self.ci, bp, e2c, e2r)
+            self.x_local = x_full
+            self.local_rows, self.local_edges, self.row_base = n, self.nnz, 0
+        else:
+            self.panel = RowPanel(self.rp, self.ci, rank, world, device=dev)
+            self.graph = self.panel.graph
+            self.row_base = self.panel.row_base
+            self.x_local = x_full[self.row_base:self.row_base + self.panel.num_rows].contiguous()
+            self.local_rows, self.local_edges = self.panel.num_rows, self.panel.num_edges
+            del x_full
+        torch.cuda.synchronize()
+        self.t_sgt = time.perf_counter() - t0
+        self.attention_w = torch.full((1, 1), 0.01, device=dev)
+        self.pre = self.dim % 4 == 0   # round the local panel before the exchange: nobody re-rounds the gathered matrix
+        self.info = None
+
+    def string(self):
+        return workload_string(self.name, self.n, self.nnz, self.dim, self.op, self.seed, self.kind)
+
+    # ---- device-resident ops
+    def kernels(self, x, attention_w=None):
+        """world == 1: x is the whole feature matrix; world > 1: the gathered matrix (legacy exchange)."""
+        T, g = self.TCGNN, self.graph
+        aw = self.attention_w if attention_w is None else attention_w
+        if self.world == 1:
+            if self.op == "spmm":
+                return T.forward(x, *g)[0]
+            if self.op == "sddmm":
+                return T.forward_ef(x, *g)[0]
+            return T.forward_AGNN_fused(x, g[0], g[1], aw, g[2], g[3], g[4], False)[0]
+        p = self.panel
+        if self.op == "spmm":
+            return p.spmm(x, x_is_tf32=self.pre)
+        ef = p.sddmm(x, x_is_tf32=self.pre)
+        if self.op == "sddmm":
+            return ef
+        att = torch.mm(ef.unsqueeze(-1), aw).transpose(0, 1).contiguous()
+        return p.spmm(x, att, x_is_tf32=self.pre)
+
+    def step_from(self, x_local, attention_w=None):
+        """One step of the measured path from this rank's feature rows."""
+        if self.world == 1:
+            return self.kernels(x_local, attention_w)
+        if self.op == "spmm":
+            return self.panel.aggregate(x_local)          # overlapped exchange + per-source-panel products
+        return self.kernels(self.panel.all_gather(x_local, round_tf32=self.pre), attention_w)
+
+    def step(self):
+        return self.step_from(self.x_local)
+
+    def exchange_label(self):
+        if self.world == 1:
+            return "single GPU"
+        st = self.panel.overlap_stats(self.dim) if self.op == "spmm" else None
+        if st is not None:
+            return (f"{self.world} destination-row panels; per step every GPU pushes its TF32-rounded panel rows to its "
+                    f"peers with the copy engines over NVLink into symmetric memory (+ a flag), the kernels add one "
+                    f"partial product per source panel as its rows land (torch.distributed/NCCL: setup only)")
+        mode = os.environ.get("TCGNN_EXCHANGE", "auto")
+        return (f"{self.world} destination-row panels; per step one exchange of X fused with the TF32 rounding pass "
+                f"(symmetric memory, P2P pushes / multicast; TCGNN_EXCHANGE={mode}), then the panel kernels")
+
+    # ---- parity of the measured path, bit for bit, on integer data
+    def parity(self):
+        import torch.distributed as dist
+        dev, n, d = self.dev, self.n, self.dim
+        gen = torch.Generator(device=dev).manual_seed(4242)
+        rp_l, ci_l = self.graph[0], self.graph[1]
+        a_rows = self.local_rows
+        out = {"checked": True, "ranks": self.world}
+        if self.op == "spmm":
+            xi = torch.randint(-8, 9, (n, d), generator=gen, device=dev).float()
+            y = self.step_from(xi[self.row_base:self.row_base + a_rows].contiguous())
+            a = torch.sparse_csr_tensor(rp_l.long(), ci_l.long(),
+                                        torch.ones(ci_l.numel(), dtype=torch.float64, device=dev), size=(a_rows, n))
+            diff = 0.0
+            for c0 in range(0, d, 32):
+                want = torch.sparse.mm(a, xi[:, c0:c0 + 32].double())
+                diff = max(diff, float((y[:, c0:c0 + 32].double() - want).abs().max()) if a_rows else 0.0)
+                del want
+            out.update({"max_abs_diff": diff, "checker": "torch.sparse.mm in fp64 on integer features in [-8, 8] "
+                                                         "(every partial sum exact in TF32/fp32): bit-exact means 0"})
+        else:
+            # +-1 features, attention_w = 1: scores are integers <= D (exact in TF32), Y exact in fp32
+            xi = (torch.randint(0, 2, (n, d), generator=gen, device=dev) * 2 - 1).float()
+            one = torch.ones(1, 1, device=dev)
+            x_loc = xi[self.row_base:self.row_base + a_rows].contiguous()
+            e2r = self.graph[4]
+            w = torch.empty(ci_l.numel(), device=dev)
+            step = 1 << 21
+            for s0 in range(0, ci_l.numel(), step):
+                w[s0:s0 + step] = (x_loc[e2r[s0:s0 + step].long()] * xi[ci_l[s0:s0 + step].long()]).sum(dim=1)
+            got = self.step_from(x_loc, one)
+            if self.op == "sddmm":
+                diff = float((got - w).abs().max()) if w.numel() else 0.0
+                out["checker"] = "gathered dot products on +-1 features (exact integers)"
+            else:
+                a = torch.sparse_csr_tensor(rp_l.long(), ci_l.long(), w.double(), size=(a_rows, n))
+                diff = 0.0
+                for c0 in range(0, d, 32):
+                    want = torch.sparse.mm(a, xi[:, c0:c0 + 32].double())
+                    diff = max(diff, float((got[:, c0:c0 + 32].double() - want).abs().max()) if a_rows else 0.0)
+                    del want
+                out["checker"] = ("fused SDDMM -> x1 -> weighted SpMM on +-1 features against gathered dot products + "
+                                  "torch.sparse.mm in fp64 (exact integers)")
+            out["max_abs_diff"] = diff
+        if self.world > 1:
+            t = torch.tensor([out["max_abs_diff"]], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            out["max_abs_diff"] = float(t.item())
+            if self.op == "spmm":
+                self.panel.overlap_check()
+        out["bit_exact"] = out["max_abs_diff"] == 0.0
+        return out
+
+
+def run_variant(name, op, dim, args, world, rank, dev, flush, with_reference):
+    """A secondary workload inside the same line: device-timed ms, parity, optionally the reference's kernels."""
+    wl = Workload(name, op, dim, args.seed, world, rank, dev)
+    wl.step()
+    torch.cuda.synchronize()
+    steps = max(5, min(args.steps, 10))
+    ms, _ = timed_steps(wl.step, steps, 3, flush, world)
+    v = {"workload": wl.string(), "ms_per_step": round(float(ms.sum()) / steps, 4), "steps": steps,
+         "value": wl.nnz / (float(ms.sum()) / steps * 1e-3), "unit": "edges/s", "n_gpus": world,
+         "parity": wl.parity()}
+    if world == 1:
+        info = wl.TCGNN.plan_info(*wl.graph)
+        v["tc_blocks"] = int(info[3])
+        v["nnz_per_tc_block"] = round(wl.nnz / max(int(info[3]), 1), 2)
+    else:
+        st = wl.panel.overlap_stats(wl.dim) if op == "spmm" else None
+        if st is not None:
+            t = torch.tensor([st["recv_bytes"], st["full_gather_rows"] * wl.dim * 4], dtype=torch.float64, device=dev)
+            import torch.distributed as dist
+            dist.all_reduce(t)
+            v["exchange"] = {"bytes_received_all_ranks": int(t[0]), "full_all_gather_bytes": int(t[1]),
+                             "packed_sources_rank0": st["packed_sources"], "dense_sources_rank0": st["dense_sources"]}
+    if with_reference and world == 1 and rank == 0:
+        ref = load_reference_module()
+        if ref is not None and op == "spmm" and wl.dim <= 128 and wl.dim % 16 == 0:
+            rp_p, n_p = pad_graph_for_reference(wl.rp, wl.n)
+            g = wl.graph
+            bp_p = torch.cat([g[2], torch.ones((n_p + 15) // 16 - g[2].numel(), dtype=torch.int32, device=dev)])
+            x_p = torch.cat([wl.x_local, torch.zeros(n_p - wl.n, wl.dim, device=dev)]).contiguous()
+            g_ref = (rp_p, wl.ci, bp_p, g[3], g[4])
+            rms, _ = timed_steps(lambda: ref.forward(x_p, *g_ref)[0], 3, 1, flush, 1)
+            y_ref = ref.forward(x_p, *g_ref)[0][:wl.n]
+            y_new = wl.step()
+            v["reference_gpu"] = {"ms_per_step": round(float(np.mean(rms)), 4),
+                                  "speedup_device": round(float(np.mean(rms)) / v["ms_per_step"], 2),
+                                  "max_abs_diff_vs_ours": float((y_ref - y_new).abs().max()),
+                                  "max_abs_ref": float(y_ref.abs().max()),
+                                  "what": "unmodified reference TCGNN_conv kernel (oracle/_ref) on the same GPU, same "
+                                          "graph and features, device-timed"}
+    wl.TCGNN.clear_plan_cache()
+    del wl
+    torch.cuda.empty_cache()
+    return v
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -243,7 +474,8 @@ def main():
     ap.add_argument("--dim", type=int, default=0, help="feature width (default: the workload's)")
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-reference-gpu", action="store_true")
+    ap.add_argument("--no-variants", action="store_true", help="skip the secondary workloads of the default line")
+    ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -273,81 +505,21 @@ def main():
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # stdout carries exactly one JSON line
         dist.init_process_group("nccl", device_id=dev)
     import TCGNN  # raises if the extension was not built: no fallback
-    from sharding import RowPanel
 
+    wl = Workload(args.workload, args.op, dim, args.seed, world, rank, dev)
+    nnz = wl.nnz
     t0 = time.perf_counter()
-    rp, ci = graphgen.synthetic_graph(n, target_nnz, kind=kind, seed=args.seed, device=dev)
-    nnz = int(ci.numel())
-    torch.cuda.synchronize()
-    t_graph = time.perf_counter() - t0
-    x_full = graphgen.features(n, dim, seed=args.seed, device=dev)
-
-    t0 = time.perf_counter()
-    panel = None
-    if world == 1:
-        bp = torch.zeros((n + 15) // 16, dtype=torch.int32, device=dev)
-        e2c = torch.zeros(nnz, dtype=torch.int32, device=dev)
-        e2r = torch.zeros(nnz, dtype=torch.int32, device=dev)
-        devnull = os.open(os.devnull, os.O_WRONLY)   # TCGNN.preprocess printf()s TC_Blocks like the reference
-        saved = os.dup(1)
-        os.dup2(devnull, 1)
-        try:
-            TCGNN.preprocess_gpu(ci, rp, n, 16, 8, bp, e2c, e2r)
-        finally:
-            os.dup2(saved, 1)
-            os.close(saved)
-            os.close(devnull)
-        graph = (rp, ci, bp, e2c, e2r)
-        x_local = x_full
-        local_rows, local_edges = n, nnz
-    else:
-        panel = RowPanel(rp, ci, rank, world, device=dev)
-        graph = panel.graph
-        x_local = x_full[panel.row_base:panel.row_base + panel.num_rows].contiguous()
-        local_rows, local_edges = panel.num_rows, panel.num_edges
-        del x_full
-    torch.cuda.synchronize()
-    t_sgt = time.perf_counter() - t0
-    info = TCGNN.plan_info(*graph) if world == 1 else None
-    attention_w = torch.full((1, 1), 0.01, device=dev)
-
-    # ---------------------------------------------------------------- the step
-    if world == 1:
-        def kernels(x):
-            if args.op == "spmm":
-                return TCGNN.forward(x, *graph)[0]
-            ef = TCGNN.forward_ef(x, *graph)[0]
-            if args.op == "sddmm":
-                return ef
-            att = torch.mm(ef.unsqueeze(-1), attention_w).transpose(0, 1).contiguous()
-            return TCGNN.forward_AGNN(x, graph[0], graph[1], att, *graph[2:])[0]
-
-        def step():
-            return kernels(x_local)
-    else:
-        pre = dim % 4 == 0   # round the local panel before the exchange: nobody re-rounds the gathered matrix
-
-        def kernels(x_all):
-            if args.op == "spmm":
-                return panel.spmm(x_all, x_is_tf32=pre)
-            ef = panel.sddmm(x_all, x_is_tf32=pre)
-            if args.op == "sddmm":
-                return ef
-            att = torch.mm(ef.unsqueeze(-1), attention_w).transpose(0, 1).contiguous()
-            return panel.spmm(x_all, att, x_is_tf32=pre)
-
-        def step():
-            return kernels(panel.all_gather(x_local, round_tf32=pre))
-
-    t0 = time.perf_counter()
-    out = step()          # builds the plan (once per graph)
+    out = wl.step()          # builds the plan(s) (once per graph)
     torch.cuda.synchronize()
     t_plan = time.perf_counter() - t0
+    if world > 1:
+        dist.barrier()
+    info = TCGNN.plan_info(*wl.graph) if world == 1 else None
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
 
     # ---------------------------------------------------------------- device-timed throughput
     sampler = ClockSampler(torch.cuda.current_device()) if rank == 0 else None
-    ms, clocks = timed_steps(step, args.steps, args.warmup, flush, world, sampler,
+    ms, clocks = timed_steps(wl.step, args.steps, args.warmup, flush, world, sampler,
                              on_timed_start=lambda: TCGNN.launch_count(True))   # count the K timed steps only
     launches = TCGNN.launch_count(True)
     total_ms = float(ms.sum())
@@ -356,71 +528,98 @@ def main():
 
     # ---------------------------------------------------------------- kernel-only (roofline)
     if world == 1:
-        k_in = x_local
+        kms, _ = timed_steps(wl.step, args.steps, 3, flush, 1)
     else:
-        k_in = panel.all_gather(x_local, round_tf32=pre)
-    kms, _ = timed_steps(lambda: kernels(k_in), args.steps, 3, flush, 1)
+        k_in = wl.panel.all_gather(wl.x_local, round_tf32=wl.pre)
+        kms, _ = timed_steps(lambda: wl.kernels(k_in), args.steps, 3, flush, 1)   # panel kernels on a gathered matrix
     k_ms = float(np.mean(kms))
     peak, peak_src = measured_peaks()
-    alg = algorithmic_bytes(args.op, local_rows, local_edges, dim)
+    alg = algorithmic_bytes(args.op, wl.local_rows, wl.local_edges, dim)
     achieved = alg / (k_ms * 1e-3) / 1e9
-    key = {"spmm": "spmm_tc_kernel", "sddmm": "sddmm_tc_kernel", "agnn": "spmm_tc_kernel"}[args.op]
+    key = {"spmm": "spmm_tc_kernel", "sddmm": "sddmm_tc_kernel", "agnn": "sddmm_tc_kernel+spmm_tc_kernel"}[args.op]
     traffic = ncu_traffic(f"{key}:{args.workload}:D{dim}") if world == 1 else None
+    tiles = int(info[3]) if info is not None else None
+    x_fits = n * dim * 4 < 100e6
     roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                 "frac": round(achieved / peak, 4), "traffic": traffic,
                 "kernel": key, "kernel_ms": round(k_ms, 4), "algorithmic_bytes": alg,
                 "peak_source": peak_src,
-                "useful_gflops": round(2.0 * local_edges * dim * (2 if args.op == "agnn" else 1) / (k_ms * 1e-3) / 1e9, 1),
+                "useful_gflops": round(2.0 * wl.local_edges * dim * (2 if args.op == "agnn" else 1) / (k_ms * 1e-3) / 1e9, 1),
                 "note": "kernel_ms = the operator's launches (tf32 round/pack + clear of split windows + " + key + ", the "
-                        "last one ~98 % of it: profiles/*launches*.csv), CUDA events, L2 flushed; algorithmic bytes = "
-                        "no-reuse CSR gather model E(4D+4)+N(4D+4) (SURVEY.md 8d); X "
-                        + ("nearly fits" if n * dim * 4 < 126e6 else "does not fit") + " in the 126 MB L2 and condensed "
-                        "tiles fetch a column once per window, so DRAM `traffic` is below the algorithmic bytes and frac "
-                        "can exceed 1 -- the physical bound is then L2->SM gather bandwidth (see `l2_gather`)"}
-    if info is not None and args.op in ("spmm", "agnn", "sddmm"):
-        # bytes the kernel actually pulls through L2: 8 feature rows per 16x8 TC block (+ SDDMM: the window's own
-        # 16 rows per 16 blocks), against the ~6300 B/clk full-chip LTS cap of B300_MICROARCH.md at the SM clock
-        tiles = int(info[3])
+                        "last ~98 % of it: profiles/*launches*.csv), CUDA events, L2 flushed; algorithmic bytes = "
+                        "no-reuse CSR gather model E(4D+4)+N(4D+4) (SURVEY.md 8d).  " +
+                        ("X fits the L2 here, so most gathers are L2 hits: frac is above what HBM alone could deliver "
+                         "and the binding resource is L2->SM gather bandwidth (`l2_gather`); `dram_frac` says how "
+                         "busy HBM really was" if x_fits else
+                         "X does not fit the L2: gathers of cold rows come from HBM, hub rows from L2")}
+    if tiles is not None:
+        comp = compulsory_bytes(args.op, wl.local_rows, n, wl.local_edges, dim, tiles)
+        roofline["compulsory_bytes"] = comp
+        roofline["compulsory_frac"] = round(comp / (k_ms * 1e-3) / 1e9 / peak, 4)
+        if traffic:
+            roofline["dram_frac"] = round(traffic / (k_ms * 1e-3) / 1e9 / peak, 4)
+            roofline["traffic_over_compulsory"] = round(traffic / comp, 2)
+        # bytes the kernels actually pull through L2: 8 feature rows per 16x8 TC block (+ SDDMM: the window's own
+        # 16 rows per 16 blocks), against the L2 -> SM gather ceiling measured with the same access shape
         per_tile = 8 * dim * 4 * (1 if args.op == "spmm" else (2.125 if args.op == "agnn" else 1.125))
         sm_clk = (clocks or {}).get("sm_mhz") or 1965.0
-        cap = 6300.0 * sm_clk * 1e6 / 1e9
+        bpc, bpc_src = measured_l2_gather_peak()
+        cap = bpc * sm_clk * 1e6 / 1e9
         l2 = tiles * per_tile / (k_ms * 1e-3) / 1e9
         roofline["l2_gather"] = {"bytes": int(tiles * per_tile), "achieved": round(l2, 1), "peak": round(cap, 1),
-                                 "unit": "GB/s", "frac": round(l2 / cap, 4),
-                                 "peak_source": "B300_MICROARCH.md LTS cap ~6300 B/clk x sampled SM clock"}
+                                 "unit": "GB/s", "frac": round(l2 / cap, 4), "peak_bytes_per_clk": bpc,
+                                 "peak_source": bpc_src + " x sampled SM clock"}
+
+    # ---------------------------------------------------------------- parity of the timed path
+    parity = wl.parity()
 
     # ---------------------------------------------------------------- end to end (host buffers)
-    x_host = x_local.cpu().pin_memory()
-    out_shape = tuple(out.shape)
-    y_host = torch.empty(out_shape, dtype=torch.float32).pin_memory()
+    e2e = None
+    if not args.no_e2e:
+        x_host = wl.x_local.cpu().pin_memory()
+        y_host = torch.empty(tuple(out.shape), dtype=torch.float32).pin_memory()
+        g = wl.graph
+        host_api = world == 1 and os.environ.get("TCGNN_BENCH_E2E", "host") != "torch"
+        api = {"spmm": "TCGNN.forward_host -> tcgnn_spmm_f32_host", "sddmm": "TCGNN.forward_ef_host -> tcgnn_sddmm_f32_host",
+               "agnn": "TCGNN.forward_AGNN_host -> tcgnn_agnn_f32_host"}[args.op] + " (C ABI, host buffers)"
 
-    host_api = (world == 1 and args.op == "spmm" and hasattr(TCGNN, "forward_host")
-                and os.environ.get("TCGNN_BENCH_E2E", "host") != "torch")
+        def e2e_step():
+            if host_api:
+                # the host-buffer entry points: H2D copy, kernels, D2H copy; stream-ordered, so the CUDA events around
+                # the step cover the last copy
+                if args.op == "spmm":
+                    TCGNN.forward_host(x_host, *g, y_host=y_host, sync=False)
+                elif args.op == "sddmm":
+                    TCGNN.forward_ef_host(x_host, *g, edge_out_host=y_host, sync=False)
+                else:
+                    TCGNN.forward_AGNN_host(x_host, g[0], g[1], wl.attention_w, g[2], g[3], g[4], y_host=y_host, sync=False)
+                return
+            xd = x_host.to(dev, non_blocking=True)
+            y_host.copy_(wl.step_from(xd), non_blocking=True)
 
-    def e2e_step():
-        if host_api:
-            # the host-buffer entry point (tcgnn_spmm_f32_host): H2D copy, kernels, D2H copy; stream-ordered, so the
-            # CUDA events around the step cover the last copy
-            TCGNN.forward_host(x_host, *graph, y_host=y_host, sync=False)
-            return
-        xd = x_host.to(dev, non_blocking=True)
-        y = kernels(xd) if world == 1 else kernels(panel.all_gather(xd, round_tf32=pre))
-        y_host.copy_(y, non_blocking=True)
-
-    ems, _ = timed_steps(e2e_step, args.steps, 3, flush, world)
-    e2e_ms = float(ems.sum()) / args.steps
-    h2d = x_host.numel() * 4
-    d2h = y_host.numel() * 4
-    if world > 1:
-        tot = torch.tensor([h2d, d2h], dtype=torch.float64, device=dev)
-        dist.all_reduce(tot)
-        h2d, d2h = int(tot[0]), int(tot[1])
-    e2e = {"value": nnz / (e2e_ms * 1e-3), "unit": "edges/s", "ms_per_step": round(e2e_ms, 4),
-           "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-           "api": "TCGNN.forward_host -> tcgnn_spmm_f32_host (C ABI, host buffers)" if host_api else
-                  "pinned copy + TCGNN operator + pinned copy",
-           "note": "features from pinned host memory, result back to pinned host memory, every step; the graph "
-                   "(CSR + SGT arrays + plan) stays resident like the reference's main_tcgnn.py:56-60"}
+        e2e_step()
+        torch.cuda.synchronize()
+        ems, _ = timed_steps(e2e_step, args.steps, 3, flush, world)
+        e2e_ms = float(ems.sum()) / args.steps
+        h2d = x_host.numel() * 4
+        d2h = y_host.numel() * 4
+        if world > 1:
+            tot = torch.tensor([h2d, d2h], dtype=torch.float64, device=dev)
+            dist.all_reduce(tot)
+            h2d, d2h = int(tot[0]), int(tot[1])
+        e2e = {"value": nnz / (e2e_ms * 1e-3), "unit": "edges/s", "ms_per_step": round(e2e_ms, 4),
+               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+               "api": api if host_api else "pinned copy + sharded operator (sharding.RowPanel) + pinned copy",
+               "note": "features from pinned host memory, result back to pinned host memory, every step; the graph "
+                       "(CSR + SGT arrays + plan) stays resident like the reference's main_tcgnn.py:56-60"
+                       + ("; SpMM is pipelined: X arrives in row chunks, every chunk's partial product starts when "
+                          "it has landed, finished output row ranges leave while the next is computed" if host_api and args.op == "spmm" else "")}
+        if host_api and args.op == "spmm":
+            y_chk = TCGNN.forward(wl.x_local, *g)[0]
+            TCGNN.forward_host(x_host, *g, y_host=y_host, sync=True)
+            den = float(y_chk.abs().max())
+            e2e["max_rel_diff_vs_resident"] = float((y_host.to(dev) - y_chk).abs().max()) / max(den, 1e-30)
+            del y_chk
 
     result = {
         "metric": "aggregation edges/s (" + {"spmm": "GCN SpMM", "sddmm": "AGNN SDDMM", "agnn": "AGNN SDDMM + weighted SpMM"}[args.op] + ")",
@@ -428,42 +627,46 @@ def main():
         "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "tf32", "dtype_note": "operands rounded with cvt.rna.tf32 like the reference's wmma path, fp32 "
                                        "accumulate in TMEM, fp32 in and out", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: N={n} nnz={nnz} D={dim} op={args.op} seed={args.seed} "
-                               f"({kind} graph, symmetric, generated on device)",
-                   "l2": "512 MiB L2 flush before every timed step",
-                   "parallelism": "single GPU" if world == 1 else f"{world} destination-row panels, one NCCL all-gather of X per step"},
-        "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "clocks": clocks,
-        "prep": {"graph_gen_s": round(t_graph, 3), "sgt_gpu_s": round(t_sgt, 3), "plan_first_call_s": round(t_plan, 3),
-                 "tc_blocks": int(info[3]) if info else None},
+        "config": {"workload": wl.string(), "generated": "on device, seeded",
+                   "l2": "512 MiB L2 flush before every timed step", "parallelism": wl.exchange_label()},
+        "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "parity": parity, "clocks": clocks,
+        "prep": {"graph_gen_s": round(wl.t_graph, 3), "sgt_gpu_s": round(wl.t_sgt, 3), "plan_first_call_s": round(t_plan, 3),
+                 "tc_blocks": tiles},
         "min_ms": round(float(ms.min()), 4), "median_ms": round(float(np.median(ms)), 4),
     }
+    if world > 1 and args.op == "spmm":
+        st = wl.panel.overlap_stats(dim)
+        if st is not None:
+            result["exchange"] = dict(st, kernel_ms_on_gathered_matrix=round(k_ms, 4),
+                                      note="rank 0's figures; kernel_ms = this rank's panel SpMM on an already gathered matrix")
 
-    if rank == 0 and world == 1:
-        if not args.no_reference_gpu:
-            ref = load_reference_module()
-            if ref is not None and args.op == "spmm" and dim <= 128 and dim % 16 == 0:
-                rp_p, n_p = pad_graph_for_reference(rp, n)
-                bp_p = torch.cat([graph[2], torch.ones((n_p + 15) // 16 - graph[2].numel(), dtype=torch.int32, device=dev)])
-                x_p = torch.cat([x_local, torch.zeros(n_p - n, dim, device=dev)]).contiguous()
-                g_ref = (rp_p, ci, bp_p, graph[3], graph[4])
-                rsteps = max(3, min(args.steps, 5))
-                rms, _ = timed_steps(lambda: ref.forward(x_p, *g_ref)[0], rsteps, 1, flush, 1)
-                y_ref = ref.forward(x_p, *g_ref)[0][:n]
-                y_new = kernels(x_local)
-                denom = float(y_ref.abs().max())
-                result["reference_gpu"] = {
-                    "what": "unmodified reference TCGNN_conv kernel (oracle/_ref, wmma sm_100 SASS) on the same B200, "
-                            "same graph and features, device-timed",
-                    "ms_per_step": round(float(np.mean(rms)), 4), "value": nnz / (float(np.mean(rms)) * 1e-3),
-                    "unit": "edges/s", "speedup_device": round(float(np.mean(rms)) / ms_per_step, 2),
-                    "max_abs_diff_vs_ours": float((y_ref - y_new).abs().max()), "max_abs_ref": denom}
-        if not args.no_cpu_baseline and args.op == "spmm":
+    # ---------------------------------------------------------------- CPU baseline + secondary workloads
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and args.op == "spmm":
+        try:
+            result["cpu_baseline"] = cpu_spmm_baseline(wl.rp.cpu().numpy(), wl.ci.cpu().numpy(),
+                                                       wl.x_local.cpu().numpy(), dim)
+        except Exception as exc:  # pragma: no cover
+            result["cpu_baseline"] = {"value": None, "unit": "edges/s", "cores": 0, "kind": "port",
+                                      "sample": f"failed: {exc}"}
+    default_line = args.workload == "reddit-like-rmat" and args.op == "spmm" and not args.dim
+    if default_line and not args.no_variants and os.environ.get("TCGNN_BENCH_VARIANTS", "1") != "0":
+        TCGNN.clear_plan_cache()
+        del wl, out
+        torch.cuda.empty_cache()
+        variants = {}
+        names = []
+        if world == 1:
+            names.append(("reddit-like-uniform", True))
+        if world in (1, 8):
+            names.append(("rmat-10m-200m", False))
+        for vname, with_ref in names:
             try:
-                result["cpu_baseline"] = cpu_spmm_baseline(rp.cpu().numpy(), ci.cpu().numpy(),
-                                                           x_host.numpy(), dim)
-            except Exception as exc:  # pragma: no cover
-                result["cpu_baseline"] = {"value": None, "unit": "edges/s", "cores": 0, "kind": "port",
-                                          "sample": f"failed: {exc}"}
+                variants[vname] = run_variant(vname, "spmm", 0, args, world, rank, dev, flush, with_ref)
+            except Exception as exc:  # pragma: no cover -- a secondary workload never takes the headline down
+                if world > 1:
+                    raise
+                variants[vname] = {"failed": repr(exc)}
+        result["variants"] = variants
     if rank == 0:
         print(json.dumps(result), flush=True)
     if world > 1:
@@ -484,8 +687,7 @@ def reference_arm(args, n, target_nnz, dim, kind, dev):
     ref = None if (args.impl == "reference-cpu" or not torch.cuda.is_available()) else load_reference_module()
     common = {"impl": "reference", "unit": "edges/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
               "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "data": "synthetic",
-              "config": {"workload": f"{args.workload}: N={n} nnz={nnz} D={dim} op={args.op} seed={args.seed} "
-                                     f"({kind} graph, symmetric)"},
+              "config": {"workload": workload_string(args.workload, n, nnz, dim, args.op, args.seed, kind)},
               "metric": "aggregation edges/s (GCN SpMM)" if args.op == "spmm" else f"aggregation edges/s ({args.op})"}
     if ref is None or args.op != "spmm" or dim > 128 or dim % 16 != 0:
         # CPU port: K passes over a bounded sample, all host cores

@@ -14,6 +14,15 @@ if [ ! -f "$REF/TCGNN.cpp" ]; then
   echo "[build_ref] reference sources not present at $REF -- skipping (prebuilt files are used if any)"; exit 0
 fi
 mkdir -p "$OUT"
+# The reference's own Python driver, staged UNMODIFIED next to the compiled module (same git-ignored directory, same
+# role: it is executed by tests/test_gpu_reference_driver.py on the GPU box -- where /root/reference does not exist
+# -- to show that main_tcgnn.py / gnn_conv.py / dataset.py run unchanged on top of the new `TCGNN` module).
+DRV="${TCGNN_REFERENCE_DIR:-/root/reference}"
+mkdir -p "$OUT/driver"
+for f in main_tcgnn.py gnn_conv.py dataset.py config.py; do
+  if [ -f "$DRV/$f" ]; then cp -pf "$DRV/$f" "$OUT/driver/$f"; fi
+done
+( cd "$OUT/driver" && sha256sum *.py > SHA256SUMS 2>/dev/null || true )
 PY=python
 SUFFIX=$($PY -c "import sysconfig;print(sysconfig.get_config_var('EXT_SUFFIX'))")
 TARGET="$OUT/TCGNN_ref$SUFFIX"

@@ -53,7 +53,8 @@ def partition_rows(row_ptr: torch.Tensor, world_size: int, blk_h: int = BLK_H,
     if block_partition is not None:
         cost = torch.clamp(block_partition.to(torch.int64).cpu(), min=1) + int(window_cost)
         if send_cost_per_row > 0 and world_size > 1:
-            return _partition_minmax(cost.numpy(), float(send_cost_per_row) * blk_h, world_size, n, blk_h)
+            return _partition_minmax(cost.numpy(), window_send_cost(row_ptr, world_size, send_cost_per_row, blk_h),
+                                     world_size, n, blk_h)
         pre = torch.cumsum(cost, 0)                      # cost of windows [0, w]
         total = int(pre[-1]) if pre.numel() else 0
         bounds = [0]
@@ -78,26 +79,41 @@ def partition_rows(row_ptr: torch.Tensor, world_size: int, blk_h: int = BLK_H,
     return bounds
 
 
-def _partition_minmax(compute, send_per_window: float, world: int, n: int, blk_h: int) -> List[int]:
+def window_send_cost(row_ptr: torch.Tensor, world_size: int, send_cost_per_row: float, blk_h: int = BLK_H):
+    """Send cost of every `blk_h`-row window: a row is shipped to the panels that reference it -- at most
+    min(degree, world - 1) of them on a symmetric graph -- and `send_cost_per_row` is the cost of shipping one row to
+    ALL world - 1 peers."""
+    import numpy as np
+    rp = row_ptr.to(torch.int64).cpu().numpy()
+    n = len(rp) - 1
+    deg = np.minimum(np.diff(rp), world_size - 1).astype(np.float64) / max(world_size - 1, 1)
+    nwin = (n + blk_h - 1) // blk_h
+    pad = np.zeros(nwin * blk_h, dtype=np.float64)
+    pad[:n] = deg
+    return pad.reshape(nwin, blk_h).sum(axis=1) * float(send_cost_per_row)
+
+
+def _partition_minmax(compute, send, world: int, n: int, blk_h: int) -> List[int]:
     """Window cuts minimising max over panels of max(sum compute, sum send): bisection on the bound T, greedy
     feasibility (extend a panel while both sums stay <= T)."""
     import numpy as np
     nwin = len(compute)
     pre_c = np.concatenate([[0.0], np.cumsum(compute, dtype=np.float64)])
+    pre_s = np.concatenate([[0.0], np.cumsum(send, dtype=np.float64)])
 
     def cuts(t):
         out, w = [0], 0
         for _ in range(world):
             # furthest end with compute <= t and send <= t
             hi_c = int(np.searchsorted(pre_c, pre_c[w] + t, side="right")) - 1
-            hi_s = w + int(t // send_per_window) if send_per_window > 0 else nwin
+            hi_s = int(np.searchsorted(pre_s, pre_s[w] + t, side="right")) - 1
             e = max(min(hi_c, hi_s, nwin), w)
             out.append(e)
             w = e
         return out
 
-    lo = max(pre_c[-1] / world, send_per_window * nwin / world, float(np.max(compute)) if nwin else 0.0, send_per_window)
-    hi = max(pre_c[-1], send_per_window * nwin) + 1.0
+    lo = max(pre_c[-1] / world, pre_s[-1] / world)
+    hi = max(pre_c[-1], pre_s[-1]) + 1.0
     for _ in range(60):
         mid = 0.5 * (lo + hi)
         if cuts(mid)[-1] >= nwin:
@@ -107,7 +123,6 @@ def _partition_minmax(compute, send_per_window: float, world: int, n: int, blk_h
     c = cuts(hi)
     c[-1] = nwin
     bounds = [min(w * blk_h, n) for w in c]
-    bounds[-1] = n
     last = n // blk_h * blk_h if n >= blk_h else 0
     return [0] + [min(b, last) for b in bounds[1:-1]] + [n]
 
@@ -375,7 +390,7 @@ class RowPanel:
         return self.spmm(self.all_gather(x_local, group, round_tf32=pre), x_is_tf32=pre)
 
     # ------------------------------------------------------------------ overlapped exchange (GCN path)
-    def build_source_subgraphs(self, dense_fraction: float = 0.7):
+    def build_source_subgraphs(self, dense_fraction: Optional[float] = None):
         """Split the panel's graph by SOURCE panel p: the edges whose column lies in panel p, as a CSR over the
         panel's rows whose column ids index the rows that will be shipped -- all of panel p (`dense`: ids rebased to
         the panel) or only the sorted unique referenced rows `ref` (ids = rank in `ref`).  Pure tensor code (runs on
@@ -383,6 +398,8 @@ class RowPanel:
         if self._sub is not None:
             return self._sub
         import TCGNN
+        if dense_fraction is None:   # ship a source's whole panel when at least this share of its rows is referenced
+            dense_fraction = float(os.environ.get("TCGNN_DENSE_FRACTION", "0.7"))
         ci = self.column_index.long()
         e2r = self.edgeToRow.long()
         dev = ci.device

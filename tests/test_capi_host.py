@@ -143,3 +143,37 @@ def test_optional_entry_points_validate_arguments_without_a_gpu(capi):
     assert L.tcgnn_push_rows(None, None, 0, None, None, 0, 4, None) == -1
     assert L.tcgnn_spmm_f32_ex(None, None, 0, None, None, 0, 0, 0, None) == -1
     assert L.tcgnn_sddmm_f32_ex(None, None, 0, None, 0, 0, None) == -1
+
+
+def test_round2_entry_points_validate_arguments_without_a_gpu(capi):
+    """tcgnn_agnn_f32 / tcgnn_csr_transpose / tcgnn_gather_rows / tcgnn_stream_wait_flag / the host-buffer entries
+    reject bad arguments before any CUDA call; the module exposes their torch-level counterparts."""
+    import ctypes as C
+    import TCGNN
+    L = capi.lib()
+    assert L.tcgnn_agnn_f32(None, None, 0, None, None, 0, None, None, 0, 0, None) == -1
+    assert L.tcgnn_sddmm_f32_host(None, None, 0, None, 0, None) == -1
+    assert L.tcgnn_agnn_f32_host(None, None, 0, None, None, 0, None, 0, None) == -1
+    assert L.tcgnn_csr_transpose(None, None, 4, 4, 0, None, None, None, None) == -1
+    assert b"tcgnn_csr_transpose" in L.tcgnn_last_error()
+    buf = (C.c_float * 64)()
+    addr = C.addressof(buf)
+    idx = (C.c_int32 * 4)()
+    assert L.tcgnn_gather_rows(addr, 6, C.addressof(idx), 2, addr, None) == -1       # ld % 4 != 0
+    assert L.tcgnn_gather_rows(addr + 4, 8, C.addressof(idx), 2, addr, None) == -1   # src not 16-byte aligned
+    assert L.tcgnn_gather_rows(None, 8, None, 0, None, None) == 0                    # nothing to do
+    assert L.tcgnn_stream_wait_flag(None, 1, 10, None, None) == -1
+    for nm in ("forward_AGNN_fused", "forward_AGNN_tile", "backward_T", "backward_T_AGNN", "csr_transpose",
+               "source_forward", "gather_rows", "stream_wait_flag", "forward_host", "forward_ef_host",
+               "forward_AGNN_host"):
+        assert callable(getattr(TCGNN, nm)), nm
+
+
+def test_production_library_ignores_the_profiling_switches(capi):
+    """TCGNN_ABLATE / TCGNN_TUNE / TCGNN_TRACE / TCGNN_PRESET are compiled out unless build.py --debug-switches
+    (switches that produce wrong results must not be live in the shipped library)."""
+    import subprocess
+    lib = os.path.join(ROOT, "tc-gnn_atc23_b200", "libtcgnn_b200.so")
+    strings = subprocess.run(["strings", "-a", lib], stdout=subprocess.PIPE, text=True).stdout
+    for env in ("TCGNN_ABLATE", "TCGNN_TRACE_CTA", "TCGNN_PRESET"):
+        assert env not in strings, f"{env} is reachable in the production library"

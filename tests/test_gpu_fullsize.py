@@ -1,5 +1,7 @@
-"""Parity at BASELINE.json's full sizes (reddit-sized graph: 232,965 nodes, ~114 M stored edges, D = 128)
-through size-independent properties -- the CPU oracle would need minutes here, so the checks are exact
+"""Parity at BASELINE.json's full sizes -- every named single-GPU workload: the reddit-sized graph (232,965 nodes,
+~114 M stored edges, D = 128) as R-MAT and as a uniform graph, the ogbn-products-sized R-MAT graph (2.45 M nodes,
+~123 M edges, D = 256: the two-feature-block kernel variant) and the R-MAT 10 M-node / 200 M-edge graph of the 8-GPU
+configuration (D = 256) -- through size-independent properties -- the CPU oracle would need minutes here, so the checks are exact
 characterisations instead:
 
   * SGT: inside every 16-row window, ranking the edges by column id must reproduce edgeToColumn (dense
@@ -17,16 +19,20 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 
-N, NNZ, D = 232965, 114615892, 128
+WORKLOADS = ["reddit-like-rmat", "reddit-like-uniform", "products-like-rmat", "rmat-10m-200m"]
 
 
-@pytest.fixture(scope="module")
-def reddit():
+@pytest.fixture(scope="module", params=WORKLOADS)
+def big(request):
+    """(row_ptr, col_idx, bp, e2c, e2r, N, D) of one workload; pytest groups the tests by parameter, so one graph is
+    resident at a time."""
     import torch
     import graphgen
     import TCGNN
     dev = torch.device("cuda")
-    rp, ci = graphgen.synthetic_graph(N, NNZ, kind="rmat", seed=0, device=dev)
+    N, NNZ, D, kind = graphgen.WORKLOADS[request.param]
+    torch.cuda.empty_cache()
+    rp, ci = graphgen.synthetic_graph(N, NNZ, kind=kind, seed=0, device=dev)
     e = ci.numel()
     bp = torch.zeros((N + 15) // 16, dtype=torch.int32, device=dev)
     e2c = torch.zeros(e, dtype=torch.int32, device=dev)
@@ -41,12 +47,27 @@ def reddit():
         os.close(saved)
         os.close(fd)
     torch.cuda.synchronize()
-    return rp, ci, bp, e2c, e2r
+    yield rp, ci, bp, e2c, e2r, N, D
+    TCGNN.clear_plan_cache()
+    del rp, ci, bp, e2c, e2r
+    torch.cuda.empty_cache()
 
 
-def test_sgt_full_size_is_the_window_rank_of_every_edge(reddit):
+def _fp64_spmm_equal(rp, ci, w, x, y, N):
+    """y == (A o w) x evaluated in fp64 by torch's CSR product (checker), 32 columns at a time."""
     import torch
-    rp, ci, bp, e2c, e2r = reddit
+    vals = torch.ones(ci.numel(), dtype=torch.float64, device="cuda") if w is None else w.double()
+    a = torch.sparse_csr_tensor(rp.long(), ci.long(), vals, size=(N, N))
+    for c0 in range(0, x.shape[1], 32):
+        want = torch.sparse.mm(a, x[:, c0:c0 + 32].double())
+        assert float(want.abs().max()) < 2 ** 24
+        assert torch.equal(y[:, c0:c0 + 32].double(), want), f"columns [{c0}, {c0 + 32}) differ"
+        del want
+
+
+def test_sgt_full_size_is_the_window_rank_of_every_edge(big):
+    import torch
+    rp, ci, bp, e2c, e2r, N, D = big
     e = ci.numel()
     rows = torch.repeat_interleave(torch.arange(N, device="cuda"), (rp[1:] - rp[:-1]).long())
     assert torch.equal(e2r.long(), rows)
@@ -69,29 +90,24 @@ def test_sgt_full_size_is_the_window_rank_of_every_edge(reddit):
     assert torch.equal(bp.long(), (torch.clamp(uniq_per_win, min=1) + 7) // 8)
 
 
-def test_spmm_full_size_exact_on_integer_features(reddit):
+def test_spmm_full_size_exact_on_integer_features(big):
     import torch
     import TCGNN
-    rp, ci, bp, e2c, e2r = reddit
+    rp, ci, bp, e2c, e2r, N, D = big
     g = torch.Generator(device="cuda").manual_seed(5)
     x = torch.randint(-8, 9, (N, D), generator=g, device="cuda").float()
     y = TCGNN.forward(x, rp, ci, bp, e2c, e2r)[0]
-    a = torch.sparse_csr_tensor(rp.long(), ci.long(), torch.ones(ci.numel(), dtype=torch.float64, device="cuda"),
-                                size=(N, N))
-    want = torch.zeros(N, D, dtype=torch.float64, device="cuda")
-    for c0 in range(0, D, 32):   # fp64 checker, 32 columns at a time (memory)
-        want[:, c0:c0 + 32] = torch.sparse.mm(a, x[:, c0:c0 + 32].double())
-    assert float(want.abs().max()) < 2 ** 24
-    assert torch.equal(y.double(), want)
+    _fp64_spmm_equal(rp, ci, None, x, y, N)
+    del y
     deg = (rp[1:] - rp[:-1]).float()
     yo = TCGNN.forward(torch.ones(N, 16, device="cuda"), rp, ci, bp, e2c, e2r)[0]
     assert torch.equal(yo, deg[:, None].expand(-1, 16))
 
 
-def test_spmm_full_size_linearity(reddit):
+def test_spmm_full_size_linearity(big):
     import torch
     import TCGNN
-    rp, ci, bp, e2c, e2r = reddit
+    rp, ci, bp, e2c, e2r, N, D = big
     x = torch.randn(N, D, generator=torch.Generator(device="cuda").manual_seed(6), device="cuda")
     y1 = TCGNN.forward(x, rp, ci, bp, e2c, e2r)[0]
     y2 = TCGNN.forward(x * 2, rp, ci, bp, e2c, e2r)[0]
@@ -103,24 +119,54 @@ def test_spmm_full_size_linearity(reddit):
     assert int((~same).sum()) <= 2 * 148 * 16
 
 
-def test_sddmm_and_weighted_spmm_full_size_exact_on_integer_features(reddit):
+def test_sddmm_and_weighted_spmm_full_size_exact_on_integer_features(big):
     import torch
     import TCGNN
-    rp, ci, bp, e2c, e2r = reddit
+    rp, ci, bp, e2c, e2r, N, D = big
     e = ci.numel()
     g = torch.Generator(device="cuda").manual_seed(7)
     x = torch.randint(-4, 5, (N, D), generator=g, device="cuda").float()
     ef = TCGNN.forward_ef(x, rp, ci, bp, e2c, e2r)[0]
-    step = 1 << 22
+    step = 1 << 21
     for s in range(0, e, step):
         r = e2r[s:s + step].long()
         c = ci[s:s + step].long()
         want = (x[r] * x[c]).sum(dim=1)      # integers < 2^11: exact in fp32 in any order
         assert torch.equal(ef[s:s + step], want), f"SDDMM differs in edges [{s}, {s + step})"
-    # weighted SpMM with integer weights: Y = (A o W) X, checked against the fp64 sparse product
+    del ef
+    # weighted SpMM with integer weights at the workload's full width (D = 256: both feature blocks): Y = (A o W) X,
+    # checked against the fp64 sparse product
     w = torch.randint(-3, 4, (e,), generator=g, device="cuda").float()
-    y = TCGNN.forward_AGNN(x[:, :32].contiguous(), rp, ci, w.reshape(1, -1), bp, e2c, e2r)[0]
-    a = torch.sparse_csr_tensor(rp.long(), ci.long(), w.double(), size=(N, N))
-    want = torch.sparse.mm(a, x[:, :32].double())
-    assert float(want.abs().max()) < 2 ** 24
-    assert torch.equal(y.double(), want)
+    y = TCGNN.forward_AGNN(x, rp, ci, w.reshape(1, -1), bp, e2c, e2r)[0]
+    _fp64_spmm_equal(rp, ci, w, x, y, N)
+
+
+def test_fused_agnn_full_size_matches_the_three_call_sequence(big):
+    """tcgnn_agnn_f32 (SDDMM -> x attention_w -> weighted SpMM, attention kept in tile order) against the reference's
+    sequence forward_ef -> torch.mm -> forward_AGNN (gnn_conv.py:125-132) on the same operators: identical except
+    in windows split across CTAs (reduce-add order), and exact on +-1 features with attention_w = 1."""
+    import torch
+    import TCGNN
+    from _util import assert_equal_up_to_split_windows
+    rp, ci, bp, e2c, e2r, N, D = big
+    g = torch.Generator(device="cuda").manual_seed(8)
+    x = torch.randn(N, D, generator=g, device="cuda") * 0.1
+    aw = torch.full((1, 1), 0.37, device="cuda")
+    y_f, att_tile, ef_f = TCGNN.forward_AGNN_fused(x, rp, ci, aw, bp, e2c, e2r, True)
+    ef = TCGNN.forward_ef(x, rp, ci, bp, e2c, e2r)[0]
+    assert torch.equal(ef, ef_f)
+    att = torch.mm(ef.unsqueeze(-1), aw).transpose(0, 1).contiguous()
+    y_3 = TCGNN.forward_AGNN(x, rp, ci, att, bp, e2c, e2r)[0]
+    assert_equal_up_to_split_windows(y_f, y_3, "fused AGNN vs forward_ef + mm + forward_AGNN")
+    y_b = TCGNN.forward_AGNN_tile(x, rp, ci, att_tile, bp, e2c, e2r)[0]      # the backward pass's call
+    assert_equal_up_to_split_windows(y_f, y_b, "tile-ordered weights re-used")
+    del y_f, y_3, y_b, ef, ef_f, att, att_tile
+    xi = (torch.randint(0, 2, (N, D), generator=g, device="cuda") * 2 - 1).float()
+    one = torch.ones(1, 1, device="cuda")
+    y_i = TCGNN.forward_AGNN_fused(xi, rp, ci, one, bp, e2c, e2r, False)[0]
+    step = 1 << 21
+    w = torch.empty(ci.numel(), device="cuda")
+    for s in range(0, ci.numel(), step):
+        w[s:s + step] = (xi[e2r[s:s + step].long()] * xi[ci[s:s + step].long()]).sum(dim=1)
+    assert float(w.abs().max()) <= D
+    _fp64_spmm_equal(rp, ci, w, xi, y_i, N)

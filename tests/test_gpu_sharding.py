@@ -100,8 +100,25 @@ def _nccl_worker(rank, world, port, q):
         for mode in ("nccl", "p2p", "p2p2", "auto"):
             os.environ["TCGNN_EXCHANGE"] = mode
             for _ in range(2):
-                y = p.aggregate(x_local)                           # exchange + panel SpMM
+                y = p.spmm(p.all_gather(x_local, round_tf32=True), x_is_tf32=True)   # exchange, then panel SpMM
                 ok = ok and np.array_equal(y.cpu().numpy(), want)
+        # the overlapped exchange (per-source-panel partial products behind copy-engine pushes + flags), with every
+        # source shipping its whole panel and with every source shipping packed referenced rows; several steps each
+        # (double-buffered receive area, monotonic flags)
+        os.environ["TCGNN_EXCHANGE"] = "overlap"
+        for frac in ("0.0", "2.0"):
+            os.environ["TCGNN_DENSE_FRACTION"] = frac
+            po = RowPanel(t_rp, t_ci, rank, world, bounds=p.bounds)
+            for step in range(4):
+                xs = x_local * float(step + 1)
+                y = po.aggregate(xs)
+                ok = ok and np.array_equal(y.cpu().numpy(), want * float(step + 1))
+            po.overlap_check()
+            st = po.overlap_stats(d)
+            ok = ok and st is not None and (st["packed_sources"] == world - 1 if frac == "2.0" else st["dense_sources"] == world - 1)
+            if frac == "2.0":
+                ok = ok and st["recv_rows"] <= st["full_gather_rows"]
+        os.environ["TCGNN_EXCHANGE"] = "auto"
         y2, ef = p.agnn_aggregate(x_local, torch.full((1, 1), 0.5, device="cuda"))
         torch.cuda.synchronize()
         ef_want = orc.sddmm(x, rp, ci)[p.edge_begin:p.edge_end]

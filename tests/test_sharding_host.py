@@ -161,3 +161,81 @@ def test_two_phase_exchange_chunks_tile_every_panel(world):
         assert all(a[1] <= b[0] for a, b in zip(held, held[1:]))
         rows = sum(c1 - c0 for c0, c1 in held)
         assert abs(rows - n / world) <= world            # ~1/N of the matrix whatever the panel sizes
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_partition_with_send_cost_bounds_rows_and_compute(world):
+    """With a per-row send cost the boundaries bound BOTH a panel's TC blocks and its rows (what it has to push to
+    every peer): the largest panel is smaller than under pure compute balancing, nothing is lost or duplicated."""
+    from sharding import partition_rows, window_send_cost
+    n = 60000
+    rp, ci = orc.rmat_graph(n, 1500000, seed=35)
+    bp, _, _, _ = orc.sgt(rp, ci, n)
+    t_rp, t_bp = torch.from_numpy(rp), torch.from_numpy(bp)
+    b0 = partition_rows(t_rp, world, block_partition=t_bp)
+    b1 = partition_rows(t_rp, world, block_partition=t_bp, send_cost_per_row=6.0)
+    for b in (b0, b1):
+        assert b[0] == 0 and b[-1] == n and b == sorted(b) and all(x % 16 == 0 for x in b[1:-1])
+    cost = np.maximum(bp, 1) + 3
+    sw = window_send_cost(t_rp, world, 6.0)
+    assert len(sw) == len(bp) and sw.max() <= 6.0 * 16 + 1e-9
+
+    def worst(b):
+        comp = [float(cost[b[i] // 16:(b[i + 1] + 15) // 16].sum()) for i in range(world)]
+        send = [float(sw[b[i] // 16:(b[i + 1] + 15) // 16].sum()) for i in range(world)]
+        return max(max(comp), max(send)), comp, send
+
+    w0, _, _ = worst(b0)
+    w1, comp, send = worst(b1)
+    assert w1 <= w0 + 1e-6                       # never worse than pure compute balancing on the combined bound
+    # and within one window of the unreachable ideal where both sums split perfectly
+    ideal = max(sum(comp) / world, sum(send) / world)
+    assert w1 <= 1.5 * ideal + cost.max() + sw.max()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("dense_fraction", [0.0, 2.0])
+def test_source_subgraphs_sum_to_the_panel_product(world, dense_fraction):
+    """The overlapped exchange computes Y_panel = sum_p A[panel, cols of p] . X[rows shipped by p]; the sub-graphs
+    (whole source panel, ids rebased -- or packed referenced rows, ids remapped) must reproduce the panel product.
+    Host logic only: the oracle's SpMM stands in for the kernels, the SGT is the product's host SGT."""
+    from sharding import RowPanel
+    n = 2503
+    rp, ci = orc.rmat_graph(n, 40000, seed=61)
+    x = np.random.default_rng(6).integers(-4, 5, size=(n, 8)).astype(np.float32)
+    want = orc.spmm(x, rp, ci)
+    t_rp, t_ci = torch.from_numpy(rp), torch.from_numpy(ci)
+    for rank in range(world):
+        p = RowPanel(t_rp, t_ci, rank, world)
+        subs = p.build_source_subgraphs(dense_fraction=dense_fraction)
+        y = np.zeros((p.num_rows, 8), dtype=np.float32)
+        edges = 0
+        for src, sb in enumerate(subs):
+            b0, b1 = p.bounds[src], p.bounds[src + 1]
+            s_rp, s_ci, s_bp, s_e2c, s_e2r = (t.numpy() for t in sb["graph"])
+            edges += len(s_ci)
+            if sb["dense"]:
+                assert src == rank or dense_fraction == 0.0
+                xs = x[b0:b1]
+            else:
+                ref = sb["ref_rows"].numpy()
+                assert len(ref) == sb["n_src"] and np.all(np.diff(ref) > 0) and ref.min() >= 0 and ref.max() < b1 - b0
+                xs = x[b0:b1][ref]                 # what gather_rows packs on the source rank
+            assert sb["n_src"] == len(xs)
+            if len(s_ci):
+                assert s_ci.max() < len(xs)
+                o_bp, o_e2c, o_e2r, _ = orc.sgt(s_rp, s_ci, p.num_rows)
+                assert np.array_equal(s_bp, o_bp) and np.array_equal(s_e2c, o_e2c) and np.array_equal(s_e2r, o_e2r)
+                y += orc.spmm(xs, s_rp, s_ci)[:p.num_rows] if len(xs) >= p.num_rows else _spmm_rect(xs, s_rp, s_ci)
+        assert edges == p.num_edges
+        assert np.array_equal(y, want[p.row_base:p.row_base + p.num_rows])
+
+
+def _spmm_rect(xs, rp, ci):
+    """Pattern SpMM of a rectangular CSR (more rows than source rows) in plain NumPy (checker)."""
+    y = np.zeros((len(rp) - 1, xs.shape[1]), dtype=np.float32)
+    rows = np.repeat(np.arange(len(rp) - 1), np.diff(rp))
+    key = np.unique(rows.astype(np.int64) * (ci.max() + 1 if len(ci) else 1) + ci)
+    m = ci.max() + 1 if len(ci) else 1
+    np.add.at(y, key // m, xs[key % m])
+    return y

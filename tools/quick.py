@@ -27,11 +27,24 @@ g = (rp, ci, bp, e2c, e2r)
 x = graphgen.features(n, d, device=dev)
 flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
 att = None
+aw = torch.full((1, 1), 0.01, device=dev)
+att_tile = None
+x_host = y_host = None
 def run():
     if a.op == "spmm": return TCGNN.forward(x, *g)[0]
     if a.op == "sddmm": return TCGNN.forward_ef(x, *g)[0]
+    if a.op == "agnn": return TCGNN.forward_AGNN_fused(x, rp, ci, aw, bp, e2c, e2r, False)[0]       # fused entry
+    if a.op == "agnn3":                                                                              # the three calls
+        ef = TCGNN.forward_ef(x, *g)[0]
+        return TCGNN.forward_AGNN(x, rp, ci, torch.mm(ef.unsqueeze(-1), aw).transpose(0, 1).contiguous(), bp, e2c, e2r)[0]
+    if a.op == "wspmm_tile": return TCGNN.forward_AGNN_tile(x, rp, ci, att_tile, bp, e2c, e2r)[0]   # tile-ordered weights
+    if a.op == "spmm_host": return TCGNN.forward_host(x_host, *g, y_host=y_host, sync=False)
+    if a.op == "spmm_T": return TCGNN.backward_T(x, *g)[0]
     return TCGNN.forward_AGNN(x, rp, ci, att, bp, e2c, e2r)[0]
 if a.op == "wspmm": att = torch.rand(1, e, device=dev)
+if a.op == "wspmm_tile": att_tile = TCGNN.forward_AGNN_fused(x, rp, ci, aw, bp, e2c, e2r, False)[1]
+if a.op == "spmm_host":
+    x_host = x.cpu().pin_memory(); y_host = torch.empty(n, d).pin_memory()
 run(); torch.cuda.synchronize()
 ts = []
 for _ in range(a.iters):
