@@ -649,6 +649,14 @@ def main():
             result["cpu_baseline"] = {"value": None, "unit": "edges/s", "cores": 0, "kind": "port",
                                       "sample": f"failed: {exc}"}
     default_line = args.workload == "reddit-like-rmat" and args.op == "spmm" and not args.dim
+    if rank == 0 and world == 1 and default_line and not args.no_cpu_baseline:
+        # BASELINE.json configs[0]: the reference's dgl_baseline GCN run restated on the host cores (timing only)
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "oracle"))
+            import dgl_baseline_cpu
+            result["cpu_baseline_dgl"] = dgl_baseline_cpu.run_best(n_epochs=100)
+        except Exception as exc:  # pragma: no cover
+            result["cpu_baseline_dgl"] = {"failed": repr(exc)}
     if default_line and not args.no_variants and os.environ.get("TCGNN_BENCH_VARIANTS", "1") != "0":
         TCGNN.clear_plan_cache()
         del wl, out

@@ -117,7 +117,7 @@ int tcgnn_plan_info(const tcgnn_plan* plan, int64_t info[8]) {
   info[3] = plan->num_tiles;
   info[4] = static_cast<int64_t>(sizeof(TileMeta)) * (plan->num_tiles + 1) +
             4 * (static_cast<int64_t>(plan->num_windows) + 1) + (plan->eperm ? 4LL * plan->num_pairs : 0) +
-            (plan->weight_perm ? 4LL * plan->num_pairs : 0) +
+            (plan->weight_perm ? 4LL * plan->num_pairs : 0) + (plan->sddmm_perm ? 4LL * plan->num_pairs : 0) +
             (plan->groups ? 16LL * plan->num_groups : 0);
   info[5] = plan->num_pairs;
   info[6] = plan->device;

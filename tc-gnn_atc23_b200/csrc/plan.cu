@@ -386,6 +386,7 @@ int plan_destroy(tcgnn_plan* p) {
   if (p->slice_ptr) cudaFree(p->slice_ptr);
   if (p->eperm) cudaFree(p->eperm);
   if (p->weight_perm) cudaFree(p->weight_perm);
+  if (p->sddmm_perm) cudaFree(p->sddmm_perm);
   if (p->x_round) cudaFree(p->x_round);
   if (p->groups) cudaFree(p->groups);
   if (p->flag) cudaFree(p->flag);

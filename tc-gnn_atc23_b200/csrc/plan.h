@@ -29,6 +29,7 @@ struct tcgnn_plan {
   int grid = 1;                       // persistent CTAs the kernels are launched with
   int32_t* eperm = nullptr;           // [num_pairs]   lazy (weighted SpMM / SDDMM)
   float* weight_perm = nullptr;       // [num_pairs]   lazy: edge weights in tile order
+  float* sddmm_perm = nullptr;        // [num_pairs]   lazy: SDDMM scores in tile order (before the CSR permutation)
   float* x_round = nullptr;           // lazy, grows: tf32-rounded, 16B-row-aligned copy of the current X
   size_t x_round_cap = 0;             // floats
   int4* groups = nullptr;             // [num_groups]  lazy: SDDMM work units {tile_start, ntiles, win, 0}

@@ -38,8 +38,10 @@ constexpr int kEpiWarps = 4;
 constexpr int kMmaWarp = 4;
 constexpr int kMetaWarp = 5;
 constexpr int kProducerWarp0 = 6;
-constexpr int kProducers = 5;                             // producer warp p owns the stages p, p + 5, ...
-constexpr int kWarps = kProducerWarp0 + kProducers;
+constexpr int kProducers = 5;                             // producer team p owns the stages p, p + 5, ...
+constexpr int kTeam = 2;                                  // warps per team: each gathers half of a stage's rows (one warp
+                                                          // sustains only ~6-9 B/clk of LDGSTS gathers, spmm_tc.cu)
+constexpr int kWarps = kProducerWarp0 + kProducers * kTeam;
 constexpr int kThreads = kWarps * 32;
 constexpr int kAcc = 4;
 constexpr int kGroupTiles = 16;
@@ -62,8 +64,8 @@ constexpr uint32_t kTuneXLast = 16u;                       // env TCGNN_TUNE: ga
 __global__ void __launch_bounds__(kThreads, 1)
 sddmm_tc_kernel(PlanView pv, const int4* __restrict__ groups, int32_t num_groups,
                 const float* __restrict__ x /* tf32-rounded, 16B aligned */, int64_t ldx /* % 4 == 0 */,
-                float* __restrict__ out_csr /* nullable: CSR edge order (via eperm) */,
-                float* __restrict__ out_tile /* nullable: tile order, tf32_rna(score * *scale) */,
+                float* __restrict__ out_raw /* nullable: scores, tile order */,
+                float* __restrict__ out_att /* nullable: tf32_rna(score * *scale), tile order */,
                 const float* __restrict__ scale /* nullable (1.0); device scalar */, int32_t dim, uint32_t flags) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -92,10 +94,10 @@ sddmm_tc_kernel(PlanView pv, const int4* __restrict__ groups, int32_t num_groups
   if (threadIdx.x == 0) {
     for (int s = 0; s < kMetaStages; ++s) {
       mbar_init(meta_full + 8 * s, 1);
-      mbar_init(meta_empty + 8 * s, nkc);          // the owners of the group's nkc stages have taken the row ids
+      mbar_init(meta_empty + 8 * s, nkc * kTeam);  // the owners of the group's nkc stages have taken the row ids
     }
     for (int s = 0; s < kStages; ++s) {
-      mbar_init(full + 8 * s, 1);                  // the stage's producer warp, once its copies have landed
+      mbar_init(full + 8 * s, kTeam);              // the stage's producer warps, once their copies have landed
       mbar_init(empty + 8 * s, 1);                 // tcgen05.commit
     }
     for (int b = 0; b < kAcc; ++b) {
@@ -163,13 +165,14 @@ sddmm_tc_kernel(PlanView pv, const int4* __restrict__ groups, int32_t num_groups
       // double-buffered: the barrier of group gl also orders everybody's reads of group gl-1's buffer before
       // the writes of group gl+1 into it
       named_barrier_sync(1, kEpiWarps * 32);
-      // CSR order straight from here (one coalesced read of the tile-order -> edge-id map, stores in runs of the
-      // <= 8 consecutive edges a row has inside a tile) -- no second pass over the [E] array; the fused AGNN
-      // path also / only leaves the scaled, tf32-rounded attention in tile order for the weighted SpMM.
+      // Coalesced tile-order stores only: writing CSR order from here (out[eperm[i]], 32 scattered sectors per store
+      // instruction) next to the producers' gathers made the kernel 1.2-1.9x slower (profiles/r02a_*: reddit R-MAT
+      // 4.9 -> 9.0 ms) -- the LSU is the contended unit.  The fused AGNN path needs no CSR order at all: it leaves
+      // the scaled, tf32-rounded attention right here for the weighted SpMM.
       for (int i = tid; i < n_out; i += kEpiWarps * 32) {
         const float v = __uint_as_float(lds_u32(obuf + i * 4));
-        if (out_csr != nullptr) out_csr[__ldg(pv.eperm + e0 + i)] = v;
-        if (out_tile != nullptr) out_tile[e0 + i] = tf32_rna(v * att_scale);
+        if (out_raw != nullptr) out_raw[e0 + i] = v;
+        if (out_att != nullptr) out_att[e0 + i] = tf32_rna(v * att_scale);
       }
     }
   } else if (warp == kMmaWarp) {
@@ -233,9 +236,12 @@ sddmm_tc_kernel(PlanView pv, const int4* __restrict__ groups, int32_t num_groups
     }
   } else {
     // ===================================== producers ====================================
-    const int pw = warp - kProducerWarp0;
+    const int pw = (warp - kProducerWarp0) / kTeam;   // team
+    const int member = (warp - kProducerWarp0) % kTeam;
     constexpr int kRows = 128 + TCGNN_BLK_H;          // gathered rows + the window's own rows
-    constexpr int kPerLane = kRows * 8 / 32;          // 36 16-byte vectors per lane and stage
+    constexpr int kPerLane = kRows * 8 / 32 / kTeam;  // 18 16-byte vectors per lane, stage and feature sub-block
+    static_assert((kRows * 8 / 32) % kTeam == 0, "the members of a team gather equal shares of a stage");
+    const int u_lo = member * kPerLane;
     const int nvec = (dim + 3) >> 2;                  // valid 16-byte vectors per row
     const uint64_t policy = (flags & kTuneXLast) ? l2_policy_evict_last() : l2_policy_evict_normal();
     const int v = lane & 7;                           // my vector inside the 32-feature chunk
@@ -252,7 +258,7 @@ sddmm_tc_kernel(PlanView pv, const int4* __restrict__ groups, int32_t num_groups
       int32_t node[kPerLane];                         // row u*4 + rsub of the stage image
 #pragma unroll
       for (int u = 0; u < kPerLane; ++u) {
-        const int row = u * 4 + rsub;
+        const int row = (u_lo + u) * 4 + rsub;
         node[u] = -1;
         if (row < 128) {
           if ((row >> 3) < ntiles) node[u] = static_cast<int32_t>(lds_u32(meta + (row >> 3) * 64 + (row & 7) * 4));
@@ -277,10 +283,11 @@ sddmm_tc_kernel(PlanView pv, const int4* __restrict__ groups, int32_t num_groups
       const bool second = dim - kc * kChunk > 32;            // the MMAs read the second sub-block too
 #pragma unroll
       for (int u = 0; u < kPerLane; ++u) {
-        const int row = u * 4 + rsub;
-        const uint32_t dst = (u < 32 ? a_stage + (row >> 3) * 1024 : b_stage + ((row - 128) >> 3) * 1024) +
+        const int row = (u_lo + u) * 4 + rsub;
+        const bool is_a = row < 128;
+        const uint32_t dst = (is_a ? a_stage + (row >> 3) * 1024 : b_stage + ((row - 128) >> 3) * 1024) +
                              sw128_offset(row & 7, v);
-        const uint32_t sub_step = u < 32 ? kASubBytes : kBSubBytes;
+        const uint32_t sub_step = is_a ? kASubBytes : kBSubBytes;
         const float* rowp = x + static_cast<int64_t>(node[u] >= 0 ? node[u] : 0) * ldx;
 #pragma unroll
         for (int sub = 0; sub < 2; ++sub) {
@@ -309,6 +316,14 @@ sddmm_tc_kernel(PlanView pv, const int4* __restrict__ groups, int32_t num_groups
   }
 }
 
+// tile order -> CSR edge order
+__global__ void unpermute_kernel(const int32_t* __restrict__ eperm, const float* __restrict__ in,
+                                 float* __restrict__ out, int32_t n) {
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    out[eperm[i]] = in[i];
+}
+
 }  // namespace
 
 // edge_out_csr (nullable): scores in CSR edge order.  tile_out (nullable): tf32_rna(score * *scale) in the plan's
@@ -316,8 +331,14 @@ sddmm_tc_kernel(PlanView pv, const int4* __restrict__ groups, int32_t num_groups
 int sddmm_launch(tcgnn_plan* plan, const float* x, int64_t ldx, float* edge_out_csr, float* tile_out,
                  const float* scale, int32_t dim, uint32_t op_flags, cudaStream_t stream) {
   if (plan->num_edges == 0) return TCGNN_OK;
-  int st = edge_out_csr != nullptr ? plan_ensure_eperm(plan, stream) : TCGNN_OK;
-  if (st != TCGNN_OK) return st;
+  int st = TCGNN_OK;
+  float* raw_tile = nullptr;
+  if (edge_out_csr != nullptr) {   // CSR order = tile order + one permutation pass
+    st = plan_ensure_eperm(plan, stream);
+    if (st == TCGNN_OK) st = plan_ensure_scratch(plan, &plan->sddmm_perm, static_cast<size_t>(plan->num_pairs));
+    if (st != TCGNN_OK) return st;
+    raw_tile = plan->sddmm_perm;
+  }
   st = plan_ensure_groups(plan, stream);
   if (st != TCGNN_OK) return st;
   static std::mutex attr_mu;
@@ -353,8 +374,15 @@ int sddmm_launch(tcgnn_plan* plan, const float* x, int64_t ldx, float* edge_out_
     }
   }
   sddmm_tc_kernel<<<grid, kThreads, kSmemBytes, stream>>>(plan->view(), plan->groups, plan->num_groups, xr, ldr,
-                                                         edge_out_csr, tile_out, scale, dim, kTuneXLast);
+                                                         raw_tile, tile_out, scale, dim, kTuneXLast);
   count_launch();
+  if (edge_out_csr != nullptr) {
+    int g = (plan->num_pairs + 255) / 256;
+    if (g > 148 * 16) g = 148 * 16;
+    if (g < 1) g = 1;
+    unpermute_kernel<<<g, 256, 0, stream>>>(plan->eperm, raw_tile, edge_out_csr, plan->num_pairs);
+    count_launch();
+  }
   e = cudaGetLastError();
   if (e != cudaSuccess) {
     set_last_error("sddmm kernel launch failed: %s", cudaGetErrorString(e));

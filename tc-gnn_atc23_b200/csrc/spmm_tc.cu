@@ -73,11 +73,17 @@ constexpr uint32_t kTuneDefault = kTuneXLast | kTuneMetaFirst | kTuneYStream;
 // nothing is cleared first (TCGNN_ACCUMULATE: per-source-panel partial products of the sharded path)
 constexpr uint32_t kFlagAccumulate = 1u << 24;
 
-// DBLK: 128-feature blocks per pass; G: tiles per pipeline stage; S: data stages; P: producer warps;
-// L: own stages a producer warp keeps in flight before it publishes the oldest
+// DBLK: 128-feature blocks per pass; G: tiles per pipeline stage; S: data stages; P: producer TEAMS (a team owns
+// whole stages); L: own stages a team keeps in flight before it publishes the oldest
 // STAGED: the epilogue stages a window's output in shared memory and writes it with one bulk copy
-template <int DBLK, int G, int S_, int P, int L, bool STAGED>
+// TEAM: warps per team.  Measured with tools/l2_gather_bench (profiles/r02a_*): one warp sustains only ~6-9 bytes per
+// clock of LDGSTS row gathers however many tiles it keeps in flight (8-10 outstanding 512-byte instructions), so six
+// gathering warps cap an SM at ~38-54 B/clk = 5600-8000 B/clk for the chip, while twelve reach ~10,800 and sixteen
+// ~12,400.  Two warps per stage double the gather issue rate without touching the per-stage barrier protocol.
+template <int DBLK, int G, int S_, int P, int L, bool STAGED, int TEAM = 2>
 struct Cfg {
+  static constexpr int kTeam = TEAM;
+  static constexpr int kTilesPerMember = G / TEAM;
   static constexpr bool kStaged = STAGED;
   static constexpr int kG = G;
   static constexpr int kATileBytes = DBLK * 4096;              // DBLK*4 swizzle atoms of 8 rows x 128 B
@@ -87,7 +93,7 @@ struct Cfg {
   static constexpr int kStages = S_;                           // data ring (A + B tiles)
   static constexpr int kProducers = P;
   static constexpr int kOwnLag = L;
-  static constexpr int kThreads = (kProducerWarp0 + P) * 32;
+  static constexpr int kThreads = (kProducerWarp0 + P * TEAM) * 32;
   static constexpr int kMetaStages = 16;                       // tile-record ring, prefetched far ahead of the data
   static constexpr uint32_t kTmemCols = kAcc * DBLK * 16;      // 64 / 128
   static constexpr int kBarBytes = (2 * kMetaStages + 2 * kStages + 2 * kAcc) * 8;
@@ -96,6 +102,7 @@ struct Cfg {
                                     kMetaStages * kMetaStageBytes + kBarBytes + kStages * 4 /*info words*/ + 16 +
                                     1024 /*alignment slack*/;
   static_assert(kG >= 1 && kG <= 8, "the open/close word holds 8 tile bits");
+  static_assert(G % TEAM == 0, "the members of a team gather equal shares of a stage");
   static_assert(kSmemBytes <= 232448, "exceeds the 227 KB of dynamic shared memory per CTA");
   static_assert(kMetaStages >= (L + 1) * P || kMetaStages >= 16, "records of every in-flight own stage stay resident");
   static_assert(L >= 1 && (L - 1) * P < S_, "a warp may not wait for the slot of an own stage it has not published yet");
@@ -195,10 +202,10 @@ spmm_tc_kernel(PlanView pv, const float* __restrict__ x /* tf32-rounded, 16B ali
   if (threadIdx.x == 0) {
     for (int s = 0; s < MS; ++s) {
       mbar_init(meta_full + 8 * s, 1);                // expect_tx arrive of the meta loader + the copy's bytes
-      mbar_init(meta_empty + 8 * s, 1);               // the stage's producer warp is done with the records
+      mbar_init(meta_empty + 8 * s, C::kTeam);        // the stage's producer warps are done with the records
     }
     for (int s = 0; s < S; ++s) {
-      mbar_init(full + 8 * s, 1);                     // the stage's producer warp: copies landed, B tiles written
+      mbar_init(full + 8 * s, C::kTeam);              // the stage's producer warps: copies landed, B tiles written
       mbar_init(empty + 8 * s, 1);                    // tcgen05.commit
     }
     for (int b = 0; b < kAcc; ++b) {
@@ -376,7 +383,11 @@ spmm_tc_kernel(PlanView pv, const float* __restrict__ x /* tf32-rounded, 16B ali
     }
   } else {
     // ===================================== producers ====================================
-    const int p = warp - kProducerWarp0;
+    // team `p` owns the stages p, p + P, ...; its member `member` gathers / builds the tiles [j_lo, j_lo + kTpm)
+    constexpr int kTpm = C::kTilesPerMember;
+    const int p = (warp - kProducerWarp0) / C::kTeam;
+    const int member = (warp - kProducerWarp0) % C::kTeam;
+    const int j_lo = member * kTpm;
     const int nvec = (dim + 3) >> 2;          // 16-byte vectors per feature row in this pass
     constexpr int kVecPerLane = DBLK * 8;     // 8 rows x DBLK*32 vectors / 32 lanes
     const bool skip_gather = kDebugSwitches && (flags & kAblateGather) != 0;
@@ -392,54 +403,56 @@ spmm_tc_kernel(PlanView pv, const float* __restrict__ x /* tf32-rounded, 16B ali
       const int ms = k % MS;
       const int32_t g0 = sl.t0 + k * kG;
       const int nt = min(kG, sl.t1 - g0);
-      const bool trp = tr && p == 0;
+      const bool trp = tr && p == 0 && member == 0;
       if (trp) trace_put(trace, 1, k / kProducers, 0);
       mbar_wait(meta_full + 8 * ms, (k / MS) & 1);
       if (trp) trace_put(trace, 1, k / kProducers, 1);
       const uint32_t meta = m_smem + ms * C::kMetaStageBytes;
       // B values of the stage
-      float4 bv[kG];
+      float4 bv[kTpm];
       if (wperm == nullptr) {
         // pattern: my four cells are four bits of one mask word
 #pragma unroll
-        for (int j = 0; j < kG; ++j) {
+        for (int jj = 0; jj < kTpm; ++jj) {
+          const int j = j_lo + jj;
           const uint32_t mw = (j < nt && !skip_build) ? lds_u32(meta + j * 64 + 32 + bword * 4) : 0u;
           const uint32_t nib = (mw >> bshift) & 0xFu;
-          bv[j] = make_float4((nib & 1u) ? 1.0f : 0.0f, (nib & 2u) ? 1.0f : 0.0f, (nib & 4u) ? 1.0f : 0.0f,
-                              (nib & 8u) ? 1.0f : 0.0f);
+          bv[jj] = make_float4((nib & 1u) ? 1.0f : 0.0f, (nib & 2u) ? 1.0f : 0.0f, (nib & 4u) ? 1.0f : 0.0f,
+                               (nib & 8u) ? 1.0f : 0.0f);
         }
       } else {
         // weighted: a tile's weights are one contiguous run of the tile-ordered array (mask-bit order).  One
         // coalesced load per tile (all issued before any is used), then every lane picks its <= 4 values by
         // rank with shuffles -- global load instructions are expensive next to the gathers.
-        uint32_t nibs[kG];
-        int ranks[kG];
-        int counts[kG];
-        float wv[kG];
-        const float* runs[kG];
+        uint32_t nibs[kTpm];
+        int ranks[kTpm];
+        int counts[kTpm];
+        float wv[kTpm];
+        const float* runs[kTpm];
 #pragma unroll
-        for (int j = 0; j < kG; ++j) {
-          nibs[j] = 0u;
-          ranks[j] = 0;
-          counts[j] = 0;
-          wv[j] = 0.0f;
-          runs[j] = wperm;
+        for (int jj = 0; jj < kTpm; ++jj) {
+          const int j = j_lo + jj;
+          nibs[jj] = 0u;
+          ranks[jj] = 0;
+          counts[jj] = 0;
+          wv[jj] = 0.0f;
+          runs[jj] = wperm;
           if (j < nt && !skip_build) {
             const int4 m4 = lds_v4(meta + j * 64 + 32);
             const uint32_t w0 = static_cast<uint32_t>(m4.x), w1 = static_cast<uint32_t>(m4.y),
                            w2 = static_cast<uint32_t>(m4.z), w3 = static_cast<uint32_t>(m4.w);
             const uint32_t mine = bword == 0 ? w0 : (bword == 1 ? w1 : (bword == 2 ? w2 : w3));
-            nibs[j] = (mine >> bshift) & 0xFu;
+            nibs[jj] = (mine >> bshift) & 0xFu;
             // rank of the first of my four bits among the tile's set bits (bit order r*8+c)
-            ranks[j] = __popc(mine & ((1u << bshift) - 1u)) + (bword > 0 ? __popc(w0) : 0) +
+            ranks[jj] = __popc(mine & ((1u << bshift) - 1u)) + (bword > 0 ? __popc(w0) : 0) +
                        (bword > 1 ? __popc(w1) : 0) + (bword > 2 ? __popc(w2) : 0);
-            counts[j] = __popc(w0) + __popc(w1) + __popc(w2) + __popc(w3);
-            runs[j] = wperm + static_cast<int32_t>(lds_u32(meta + j * 64 + 52));
-            if (counts[j] <= 32 && lane < counts[j]) wv[j] = __ldg(runs[j] + lane);
+            counts[jj] = __popc(w0) + __popc(w1) + __popc(w2) + __popc(w3);
+            runs[jj] = wperm + static_cast<int32_t>(lds_u32(meta + j * 64 + 52));
+            if (counts[jj] <= 32 && lane < counts[jj]) wv[jj] = __ldg(runs[jj] + lane);
           }
         }
 #pragma unroll
-        for (int j = 0; j < kG; ++j) {
+        for (int j = 0; j < kTpm; ++j) {
           const uint32_t nib = nibs[j];
           const int r0 = ranks[j], r1 = r0 + (nib & 1u), r2 = r1 + ((nib >> 1) & 1u), r3 = r2 + ((nib >> 2) & 1u);
           if (counts[j] <= 32) {   // warp-uniform
@@ -477,7 +490,8 @@ spmm_tc_kernel(PlanView pv, const float* __restrict__ x /* tf32-rounded, 16B ali
       if (trp) trace_put(trace, 1, k / kProducers, 5);
       if (!skip_gather) {
 #pragma unroll 2
-        for (int j = 0; j < kG; ++j) {
+        for (int jj = 0; jj < kTpm; ++jj) {
+          const int j = j_lo + jj;
           if (j < nt) {
             const uint32_t a_tile = a_smem + s * C::kAStageBytes + j * C::kATileBytes;
             const int4 c0 = lds_v4(meta + j * 64), c1 = lds_v4(meta + j * 64 + 16);   // rows to gather (-1: padding)
@@ -520,12 +534,12 @@ spmm_tc_kernel(PlanView pv, const float* __restrict__ x /* tf32-rounded, 16B ali
       if (trp) trace_put(trace, 1, k / kProducers, 6);
       __syncwarp();
       if (lane == 0) {
-        mbar_arrive(meta_empty + 8 * ms);             // every lane has read the records
-        sts_u32(info_smem + 4 * s, fm | (lm << 8) | (static_cast<uint32_t>(nt) << 16));
+        mbar_arrive(meta_empty + 8 * ms);             // every lane of this warp has read the records
+        if (member == 0) sts_u32(info_smem + 4 * s, fm | (lm << 8) | (static_cast<uint32_t>(nt) << 16));
       }
 #pragma unroll
-      for (int j = 0; j < kG; ++j)
-        if (j < nt) sts_v4(b_smem + s * C::kBStageBytes + j * kBTileBytes + lane * 16, bv[j]);
+      for (int jj = 0; jj < kTpm; ++jj)
+        if (j_lo + jj < nt) sts_v4(b_smem + s * C::kBStageBytes + (j_lo + jj) * kBTileBytes + lane * 16, bv[jj]);
       if (trp) trace_put(trace, 1, k / kProducers, 7);
     }
     // drain: publish the own stages still in flight
@@ -635,9 +649,16 @@ cudaError_t launch_pass(const tcgnn_plan* plan, const PlanView& pv, int grid, co
     count_launch();
   }
   constexpr int T = 8 / DBLK;   // tiles in 32 KB of A
-#define TCGNN_LAUNCH(G, S, P, STAGED) \
-  return launch_kernel<Cfg<DBLK, G, S, P, 1, STAGED>, DBLK>(plan, pv, grid, xr, ldr, wperm, y, ldy, dim, mode_flags, \
-                                                            stream)
+  // TCGNN_SPMM_TEAM=1 keeps one gathering warp per stage (the round-1 shape; a tuning knob, results are identical)
+  static const int team = [] {
+    const char* e = getenv("TCGNN_SPMM_TEAM");
+    return e != nullptr && atoi(e) == 1 ? 1 : 2;
+  }();
+#define TCGNN_LAUNCH(G, S, P, STAGED)                                                                              \
+  return team == 1 ? launch_kernel<Cfg<DBLK, G, S, P, 1, STAGED, 1>, DBLK>(plan, pv, grid, xr, ldr, wperm, y, ldy, dim, \
+                                                                         mode_flags, stream)                        \
+                   : launch_kernel<Cfg<DBLK, G, S, P, 1, STAGED, 2>, DBLK>(plan, pv, grid, xr, ldr, wperm, y, ldy, dim, \
+                                                                         mode_flags, stream)
   // Dense windows (hundreds of tiles each: reddit): the deepest ring, output written straight from registers
   // (rare).  Sparse windows: one output tile every few tiles -- stage it and hand it to the TMA engine; the
   // staging buffers cost one pipeline slot.
@@ -646,8 +667,6 @@ cudaError_t launch_pass(const tcgnn_plan* plan, const PlanView& pv, int grid, co
   switch (preset) {
     case 1: TCGNN_LAUNCH(T, 6, 6, false);
 #ifdef TCGNN_DEBUG_SWITCHES
-    case 3: TCGNN_LAUNCH(T - 1, 6, 6, true);
-    case 4: TCGNN_LAUNCH(T - 1, 6, 5, true);
     case 5: TCGNN_LAUNCH(T, 5, 4, true);
     case 6: TCGNN_LAUNCH(T, 5, 5, false);
 #endif

@@ -35,8 +35,16 @@
 
 constexpr int kDim = 128;           // floats per row: 512 B
 constexpr int kTileBytes = 8 * kDim * 4;
-constexpr int64_t kIdxTiles = 1 << 18;   // row ids of 256 K tiles (8 MB), walked from a different offset by every warp
-constexpr int64_t kIdxMask = kIdxTiles - 1;
+// row id of slot `i` (tile * 8 + row): a hash of the global slot number, so every warp gathers its own random rows and
+// nothing but the working-set size decides the L2 hit rate (a shared index ring made warps on different SMs walk the
+// same rows at the same time: profiles/r02a_l2_gather_sweep_shared_index_ring.jsonl)
+__device__ __forceinline__ int32_t row_of(uint64_t i, uint32_t rows) {
+  uint64_t h = (i + 1) * 0x9E3779B97F4A7C15ull;
+  h ^= h >> 29;
+  h *= 0xBF58476D1CE4E5B9ull;
+  h ^= h >> 32;
+  return static_cast<int32_t>(__umulhi(static_cast<uint32_t>(h), rows));
+}
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 __device__ __forceinline__ uint32_t sw128_base32_offset(uint32_t row, uint32_t chunk16) {
@@ -47,7 +55,7 @@ __device__ __forceinline__ uint32_t sw128_base32_offset(uint32_t row, uint32_t c
 // LDGSTS
 // ------------------------------------------------------------------------------------------------------------------
 template <int DEPTH>
-__global__ void gather_ldgsts(const float* __restrict__ x, const int32_t* __restrict__ idx, int tiles_per_warp,
+__global__ void gather_ldgsts(const float* __restrict__ x, uint32_t rows, int tiles_per_warp,
                               unsigned long long* max_cycles, float* dump) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -55,10 +63,8 @@ __global__ void gather_ldgsts(const float* __restrict__ x, const int32_t* __rest
   const uint32_t ring = smem + warp * DEPTH * kTileBytes;
   const long long t0 = clock64();
   const int64_t first = (static_cast<int64_t>(blockIdx.x) * warps + warp) * tiles_per_warp;
-  int32_t next_row = lane < 8 ? __ldg(idx + (first & kIdxMask) * 8 + lane) : 0;
   for (int i = 0; i < tiles_per_warp; ++i) {
-    const int32_t my_row = next_row;
-    if (i + 1 < tiles_per_warp && lane < 8) next_row = __ldg(idx + ((first + i + 1) & kIdxMask) * 8 + lane);
+    const int32_t my_row = row_of(static_cast<uint64_t>(first + i) * 8 + (lane & 7), rows);
     if (i >= DEPTH) asm volatile("cp.async.wait_group %0;" ::"n"(DEPTH - 1) : "memory");
     const uint32_t tile = ring + (i % DEPTH) * kTileBytes;
 #pragma unroll
@@ -119,7 +125,7 @@ __device__ __forceinline__ void gather4(uint32_t dst, const CUtensorMap* map, in
 
 // WIDE = false: swizzled 128-byte boxes into the MMA image (8 instructions per tile); true: 512-byte boxes, row-major
 template <int DEPTH, bool WIDE>
-__global__ void gather_tma(const __grid_constant__ CUtensorMap map, const int32_t* __restrict__ idx, int tiles_per_warp,
+__global__ void gather_tma(const __grid_constant__ CUtensorMap map, uint32_t rows, int tiles_per_warp,
                            unsigned long long* max_cycles, float* dump) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -136,8 +142,9 @@ __global__ void gather_tma(const __grid_constant__ CUtensorMap map, const int32_
     for (int i = 0; i < tiles_per_warp; ++i) {
       const int s = i % DEPTH;
       if (i >= DEPTH) mbar_wait(bars + 8 * s, ((i / DEPTH) - 1) & 1);   // the slot's previous tile has landed
-      const int4 ra = __ldg(reinterpret_cast<const int4*>(idx + ((first + i) & kIdxMask) * 8));
-      const int4 rb = __ldg(reinterpret_cast<const int4*>(idx + ((first + i) & kIdxMask) * 8 + 4));
+      const uint64_t t8 = static_cast<uint64_t>(first + i) * 8;
+      const int4 ra = make_int4(row_of(t8, rows), row_of(t8 + 1, rows), row_of(t8 + 2, rows), row_of(t8 + 3, rows));
+      const int4 rb = make_int4(row_of(t8 + 4, rows), row_of(t8 + 5, rows), row_of(t8 + 6, rows), row_of(t8 + 7, rows));
       const uint32_t tile = ring + s * kTileBytes;
       mbar_expect(bars + 8 * s, kTileBytes);
       if (WIDE) {
@@ -190,14 +197,9 @@ static bool make_map(CUtensorMap* map, float* x, int64_t rows, bool wide) {
   return r == CUDA_SUCCESS;
 }
 
-__global__ void fill_kernel(float* x, int64_t n, int32_t* idx, int64_t n_idx, int64_t rows) {
+__global__ void fill_kernel(float* x, int64_t n) {
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * blockDim.x)
     x[i] = static_cast<float>((i * 2654435761ull) & 0xFFFF) * (1.0f / 65536.0f);
-  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n_idx; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    uint64_t h = (i + 1) * 0x9E3779B97F4A7C15ull;
-    h ^= h >> 29; h *= 0xBF58476D1CE4E5B9ull; h ^= h >> 32;
-    idx[i] = static_cast<int32_t>(h % static_cast<uint64_t>(rows));
-  }
 }
 
 struct Result { double ms, gbs, bpc; };
@@ -228,7 +230,7 @@ static Result time_it(Launch launch, unsigned long long* d_cyc, double bytes, in
 }
 
 template <int DEPTH>
-static void run_depth(const char* mode, int warps, float* x, int32_t* idx, const CUtensorMap* map, int tiles_per_warp,
+static void run_depth(const char* mode, int warps, float* x, uint32_t idx, const CUtensorMap* map, int tiles_per_warp,
                       int grid, unsigned long long* d_cyc, double ws_mb, float* dump) {
   const size_t smem = static_cast<size_t>(warps) * DEPTH * kTileBytes + warps * DEPTH * 8 + 1024;
   if (smem > 232448) return;
@@ -260,19 +262,17 @@ int main(int argc, char** argv) {
   fprintf(stderr, "device: %s, %d SMs, L2 %d MB\n", prop.name, grid, prop.l2CacheSize >> 20);
   const int64_t max_rows = (512ll << 20) / (kDim * 4);
   float* x = nullptr;
-  int32_t* idx = nullptr;
   unsigned long long* d_cyc = nullptr;
   float* dump = nullptr;
   const int tiles_per_warp = quick ? 512 : 2048;
-  const int64_t n_idx = kIdxTiles * 8;
   CK(cudaMalloc(&x, max_rows * kDim * 4));
-  CK(cudaMalloc(&idx, n_idx * 4));
   CK(cudaMalloc(&d_cyc, 8));
   CK(cudaMalloc(&dump, 3 * kTileBytes));
   // ---- image check: the three paths gather the same 8 rows; ldgsts and gather4 must produce identical bytes
   {
     const int64_t rows = 100000;
-    fill_kernel<<<grid * 8, 256>>>(x, rows * kDim, idx, n_idx, rows);
+    const uint32_t idx = static_cast<uint32_t>(rows);
+    fill_kernel<<<grid * 8, 256>>>(x, rows * kDim);
     CK(cudaDeviceSynchronize());
     CUtensorMap map_s, map_w;
     const bool ok_s = make_map(&map_s, x, rows, false), ok_w = make_map(&map_w, x, rows, true);
@@ -298,7 +298,8 @@ int main(int argc, char** argv) {
   const int n_ws = quick ? 2 : 6;
   for (int wi = 0; wi < n_ws; ++wi) {
     const int64_t rows = static_cast<int64_t>(ws_list[wi] * 1e6 / (kDim * 4));
-    fill_kernel<<<grid * 8, 256>>>(x, rows * kDim, idx, n_idx, rows);
+    const uint32_t idx = static_cast<uint32_t>(rows);
+    fill_kernel<<<grid * 8, 256>>>(x, rows * kDim);
     CK(cudaDeviceSynchronize());
     CUtensorMap map_s, map_w;
     const bool ok_s = make_map(&map_s, x, rows, false), ok_w = make_map(&map_w, x, rows, true);
