@@ -133,8 +133,25 @@ def measured_l2_gather_peak():
     if os.path.exists(p):
         with open(p) as fh:
             d = json.load(fh)
-        return float(d["bytes_per_clk"]), "measured (profiles/l2_gather_peak.json, tools/l2_gather_bench)"
-    return 6300.0, "B300_MICROARCH.md LTS cap ~6300 B/clk (not measured here)"
+        return float(d["bytes_per_clk"]), "measured (profiles/l2_gather_peak.json, tools/l2_gather_bench)", d.get("curve")
+    return 6300.0, "B300_MICROARCH.md LTS cap ~6300 B/clk (not measured here)", None
+
+
+def ceiling_at(curve, x_mb):
+    """The measured gather ceiling for a feature matrix of `x_mb` MB (log-linear between the sweep's sizes)."""
+    import math
+    if not curve:
+        return None
+    pts = sorted((c["working_set_mb"], c["bytes_per_clk"]) for c in curve)
+    if x_mb <= pts[0][0]:
+        return pts[0][1]
+    if x_mb >= pts[-1][0]:
+        return pts[-1][1]
+    for (a, fa), (b, fb) in zip(pts, pts[1:]):
+        if a <= x_mb <= b:
+            t = (math.log(x_mb) - math.log(a)) / (math.log(b) - math.log(a))
+            return fa + t * (fb - fa)
+    return pts[-1][1]
 
 
 def compulsory_bytes(op, n_rows, n_cols, n_edges, dim, tiles):
@@ -563,12 +580,17 @@ def main():
         # 16 rows per 16 blocks), against the L2 -> SM gather ceiling measured with the same access shape
         per_tile = 8 * dim * 4 * (1 if args.op == "spmm" else (2.125 if args.op == "agnn" else 1.125))
         sm_clk = (clocks or {}).get("sm_mhz") or 1965.0
-        bpc, bpc_src = measured_l2_gather_peak()
+        bpc, bpc_src, curve = measured_l2_gather_peak()
         cap = bpc * sm_clk * 1e6 / 1e9
         l2 = tiles * per_tile / (k_ms * 1e-3) / 1e9
         roofline["l2_gather"] = {"bytes": int(tiles * per_tile), "achieved": round(l2, 1), "peak": round(cap, 1),
                                  "unit": "GB/s", "frac": round(l2 / cap, 4), "peak_bytes_per_clk": bpc,
-                                 "peak_source": bpc_src + " x sampled SM clock"}
+                                 "peak_source": bpc_src + " x sampled SM clock; peak = random 512-byte row gathers of an "
+                                                "L2-RESIDENT matrix (<= 64 MB)"}
+        at = ceiling_at(curve, n * dim * 4 / 1e6)
+        if at is not None:   # the same micro-benchmark on a matrix as large as this X (hit rate included)
+            roofline["l2_gather"]["peak_same_working_set"] = round(at * sm_clk * 1e6 / 1e9, 1)
+            roofline["l2_gather"]["frac_same_working_set"] = round(l2 / (at * sm_clk * 1e6 / 1e9), 4)
 
     # ---------------------------------------------------------------- parity of the timed path
     parity = wl.parity()

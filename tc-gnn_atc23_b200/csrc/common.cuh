@@ -100,6 +100,26 @@ __device__ __forceinline__ void fence_mbar_init() {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// Arrive that releases a buffer the caller has only READ: `dep` must be computed from every value loaded out of that
+// buffer and can never equal 0x80000000 (OR of non-negative ids, -1 paddings and words shifted right by one).
+// An mbarrier arrive is an independent shared-memory operation: it can complete while earlier ld.shared instructions
+// of the warp still wait in a backed-up load/store queue (the gathers keep it full), and the buffer's next writer --
+// a TMA bulk copy released by this very arrive -- then overwrites what they have yet to read.  Seen as ~1 wrong tile
+// per 10^8 in SDDMM at D = 256 (profiles/r02c_*, r02d_*).  The arrive count is computed from `dep` (always 1), so the
+// instruction cannot issue before the loads' results are in their registers -- a real register dependence, which
+// neither the compiler nor the assembler can fold away.
+__device__ __forceinline__ void mbar_arrive_after_loads(uint32_t bar, uint32_t dep) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      ".reg .b32 c;\n"
+      "setp.eq.u32 p, %1, 0x80000000;\n"
+      "selp.b32 c, 2, 1, p;\n"
+      "mbarrier.arrive.shared::cta.b64 _, [%0], c;\n"
+      "}\n" ::"r"(bar),
+      "r"(dep)
+      : "memory");
+}
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }

@@ -39,10 +39,7 @@ constexpr int kMmaWarp = 4;
 constexpr int kMetaWarp = 5;
 constexpr int kProducerWarp0 = 6;
 constexpr int kProducers = 5;                             // producer team p owns the stages p, p + 5, ...
-constexpr int kTeam = 2;                                  // warps per team: each gathers half of a stage's rows (one warp
-                                                          // sustains only ~6-9 B/clk of LDGSTS gathers, spmm_tc.cu)
-constexpr int kWarps = kProducerWarp0 + kProducers * kTeam;
-constexpr int kThreads = kWarps * 32;
+// kTeam (template parameter of the kernel): warps per team, each gathers an equal share of a stage's rows
 constexpr int kAcc = 4;
 constexpr int kGroupTiles = 16;
 constexpr int kChunk = 64;                                 // features per pipeline stage: two 32-feature sub-blocks
@@ -55,13 +52,15 @@ constexpr int kMetaStageBytes = kMetaTileBytes + 16;       // + header {tile_sta
 constexpr uint32_t kTmemCols = kAcc * 16;
 constexpr int kOutStageBytes = kGroupTiles * TCGNN_BLK_H * TCGNN_BLK_W * 4;   // a group's edge values, compacted (8 KB)
 constexpr int kSmemBytes = kStages * (kAStageBytes + kBStageBytes) + 2 * kOutStageBytes +
-                           kMetaStages * kMetaStageBytes + (2 * kMetaStages + 2 * kStages + 2 * kAcc) * 8 + 16 + 1024;
+                           kMetaStages * kMetaStageBytes + (2 * kMetaStages + 2 * kStages + 2 * kAcc) * 8 + 64 + 1024;
 static_assert(kProducers <= kStages, "a warp may not wait for the slot of an own stage it has not published yet");
 static_assert(kMetaStages >= 2 * kProducers, "one feature chunk per group: every in-flight stage is another group");
 static_assert(kSmemBytes <= 232448, "exceeds the 227 KB of dynamic shared memory per CTA");
-constexpr uint32_t kTuneXLast = 16u;                       // env TCGNN_TUNE: gathers with L2 evict_last
+constexpr uint32_t kTuneXLast = 16u;                       // gathers with L2 evict_last
+constexpr uint32_t kDbgTrailingCopy = 1u;                  // diagnostics: one more (zero-fill) cp.async closes every stage
 
-__global__ void __launch_bounds__(kThreads, 1)
+template <int kTeam>
+__global__ void __launch_bounds__((kProducerWarp0 + kProducers * kTeam) * 32, 1)
 sddmm_tc_kernel(PlanView pv, const int4* __restrict__ groups, int32_t num_groups,
                 const float* __restrict__ x /* tf32-rounded, 16B aligned */, int64_t ldx /* % 4 == 0 */,
                 float* __restrict__ out_raw /* nullable: scores, tile order */,
@@ -123,20 +122,44 @@ sddmm_tc_kernel(PlanView pv, const int4* __restrict__ groups, int32_t num_groups
     const int tt = m >> 3, c = m & 7;  // tile inside the group, column inside the tile
     const int tid = threadIdx.x;       // 0..127
     const float att_scale = scale != nullptr ? __ldg(scale) : 1.0f;
-    for (int32_t gl = 0; gl < n_groups; ++gl) {
-      const int4 grp = groups[g_lo + gl];
-      uint4 mask = make_uint4(0, 0, 0, 0);
-      int32_t edge_ofs = 0;
-      if (tt < grp.y) {   // issue the record loads before waiting for the accumulator
-        const TileMeta* t = pv.tiles + grp.x + tt;
-        mask = *reinterpret_cast<const uint4*>(t->mask);
-        edge_ofs = t->edge_ofs;
+    // The group's tile records (occupancy masks, output offsets) come from global memory through two dependent loads
+    // (work unit -> records): they are fetched one group ahead (the work unit two ahead), so their L2 latency is
+    // hidden behind the previous group's epilogue instead of sitting between "accumulator ready" and its drain --
+    // the four epilogue warps see one accumulator every two pipeline stages.
+    struct Records {
+      uint4 mask, last_mask;
+      int32_t edge_ofs, first_ofs, last_ofs, ntiles;
+    };
+    auto fetch = [&](const int4 g) {
+      Records r;
+      r.mask = make_uint4(0, 0, 0, 0);
+      r.edge_ofs = 0;
+      r.ntiles = g.y;
+      if (tt < g.y) {
+        const TileMeta* t = pv.tiles + g.x + tt;
+        r.mask = *reinterpret_cast<const uint4*>(t->mask);
+        r.edge_ofs = t->edge_ofs;
       }
       // first / one-past-last output index of the group (same addresses for all threads: broadcast loads)
-      const int32_t e0 = pv.tiles[grp.x].edge_ofs;
-      const TileMeta* tl = pv.tiles + grp.x + grp.y - 1;
-      const uint4 ml = *reinterpret_cast<const uint4*>(tl->mask);
-      const int32_t n_out = tl->edge_ofs + __popc(ml.x) + __popc(ml.y) + __popc(ml.z) + __popc(ml.w) - e0;
+      r.first_ofs = pv.tiles[g.x].edge_ofs;
+      const TileMeta* tl = pv.tiles + g.x + g.y - 1;
+      r.last_mask = *reinterpret_cast<const uint4*>(tl->mask);
+      r.last_ofs = tl->edge_ofs;
+      return r;
+    };
+    int4 g_ahead = n_groups > 1 ? groups[g_lo + 1] : make_int4(0, 1, 0, 0);
+    Records ahead = n_groups > 0 ? fetch(groups[g_lo]) : Records{};
+    for (int32_t gl = 0; gl < n_groups; ++gl) {
+      const Records rec = ahead;
+      if (gl + 1 < n_groups) {
+        ahead = fetch(g_ahead);
+        if (gl + 2 < n_groups) g_ahead = groups[g_lo + gl + 2];
+      }
+      const uint4 mask = rec.mask;
+      const int32_t edge_ofs = rec.edge_ofs;
+      const int32_t e0 = rec.first_ofs;
+      const uint4 ml = rec.last_mask;
+      const int32_t n_out = rec.last_ofs + __popc(ml.x) + __popc(ml.y) + __popc(ml.z) + __popc(ml.w) - e0;
       const int b = gl % kAcc;
       mbar_wait_backoff(acc_full + 8 * b, (gl / kAcc) & 1);
       tc_fence_after();
@@ -267,8 +290,12 @@ sddmm_tc_kernel(PlanView pv, const int4* __restrict__ groups, int32_t num_groups
           node[u] = r < pv.num_nodes ? r + pv.row_base : -1;   // the window's own rows (global ids)
         }
       }
+      // the ring slot may be refilled as soon as this arrive lands: every row id must be IN its register first
+      uint32_t dep = static_cast<uint32_t>(ntiles ^ win);
+#pragma unroll
+      for (int u = 0; u < kPerLane; ++u) dep |= static_cast<uint32_t>(node[u]);
       __syncwarp();
-      if (lane == 0) mbar_arrive(meta_empty + 8 * ms);
+      if (lane == 0) mbar_arrive_after_loads(meta_empty + 8 * ms, dep);
       // publish the previous own stage once its copies have landed -- BEFORE blocking on a free slot
       if (k - published >= kProducers) {
         cp_async_wait_group<0>();
@@ -297,6 +324,7 @@ sddmm_tc_kernel(PlanView pv, const int4* __restrict__ groups, int32_t num_groups
           cp_async_16_hint(dst + sub * sub_step, rowp + (valid ? vg * 4 : 0), valid ? 16u : 0u, policy);  // zero-fill
         }
       }
+      if (flags & kDbgTrailingCopy) cp_async_16(tmem_slot + 16 + (lane & 1) * 16, x, 0u);
       cp_async_commit_group();
       kc += kProducers;
       while (kc >= nkc) { kc -= nkc; ++gl; }
@@ -341,13 +369,25 @@ int sddmm_launch(tcgnn_plan* plan, const float* x, int64_t ldx, float* edge_out_
   }
   st = plan_ensure_groups(plan, stream);
   if (st != TCGNN_OK) return st;
+  // warps per producer team: a tuning knob (results are identical), TCGNN_SDDMM_TEAM=1|2|3
+  static const int team = [] {
+    const char* e = getenv("TCGNN_SDDMM_TEAM");
+    const int v = e ? atoi(e) : 2;
+    return v >= 1 && v <= 3 ? v : 2;
+  }();
+  static const uint32_t dbg = [] {
+    const char* e = getenv("TCGNN_SDDMM_DBG");
+    return e ? static_cast<uint32_t>(atoi(e)) & kDbgTrailingCopy : 0u;
+  }();
   static std::mutex attr_mu;
   static bool attr_set[64] = {};
   cudaError_t e;
   {
     std::lock_guard<std::mutex> lock(attr_mu);
     if (plan->device >= 64 || !attr_set[plan->device]) {
-      e = cudaFuncSetAttribute(sddmm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+      e = cudaFuncSetAttribute(sddmm_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(sddmm_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(sddmm_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
       if (e != cudaSuccess) {
         set_last_error("cudaFuncSetAttribute(sddmm) failed: %s", cudaGetErrorString(e));
         return TCGNN_ERR_CUDA;
@@ -373,8 +413,15 @@ int sddmm_launch(tcgnn_plan* plan, const float* x, int64_t ldx, float* edge_out_
       return TCGNN_ERR_CUDA;
     }
   }
-  sddmm_tc_kernel<<<grid, kThreads, kSmemBytes, stream>>>(plan->view(), plan->groups, plan->num_groups, xr, ldr,
-                                                         raw_tile, tile_out, scale, dim, kTuneXLast);
+  const PlanView pv = plan->view();
+  const uint32_t kflags = kTuneXLast | dbg;
+#define TCGNN_SDDMM(T)                                                                                      \
+  sddmm_tc_kernel<T><<<grid, (kProducerWarp0 + kProducers * T) * 32, kSmemBytes, stream>>>(                \
+      pv, plan->groups, plan->num_groups, xr, ldr, raw_tile, tile_out, scale, dim, kflags)
+  if (team == 1) TCGNN_SDDMM(1);
+  else if (team == 3) TCGNN_SDDMM(3);
+  else TCGNN_SDDMM(2);
+#undef TCGNN_SDDMM
   count_launch();
   if (edge_out_csr != nullptr) {
     int g = (plan->num_pairs + 255) / 256;

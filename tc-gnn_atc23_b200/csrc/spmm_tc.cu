@@ -105,7 +105,10 @@ struct Cfg {
   static_assert(G % TEAM == 0, "the members of a team gather equal shares of a stage");
   static_assert(kSmemBytes <= 232448, "exceeds the 227 KB of dynamic shared memory per CTA");
   static_assert(kMetaStages >= (L + 1) * P || kMetaStages >= 16, "records of every in-flight own stage stay resident");
-  static_assert(L >= 1 && (L - 1) * P < S_, "a warp may not wait for the slot of an own stage it has not published yet");
+  // L == 0: a team publishes the stage it has just filled as soon as its copies have landed (it sits in
+  // cp.async.wait_group for the tail of the flight and builds the next stage's B values afterwards, while the MMAs
+  // consume this one); L >= 1: the stage is published at the top of the L-th following own iteration.
+  static_assert(L >= 0 && (L - 1) * P < S_, "a warp may not wait for the slot of an own stage it has not published yet");
 };
 
 struct SliceInfo {
@@ -410,12 +413,14 @@ spmm_tc_kernel(PlanView pv, const float* __restrict__ x /* tf32-rounded, 16B ali
       const uint32_t meta = m_smem + ms * C::kMetaStageBytes;
       // B values of the stage
       float4 bv[kTpm];
+      uint32_t ring_dep = 0u;   // every word read from the record ring, see mbar_arrive_after_loads
       if (wperm == nullptr) {
         // pattern: my four cells are four bits of one mask word
 #pragma unroll
         for (int jj = 0; jj < kTpm; ++jj) {
           const int j = j_lo + jj;
           const uint32_t mw = (j < nt && !skip_build) ? lds_u32(meta + j * 64 + 32 + bword * 4) : 0u;
+          ring_dep |= mw >> 1;
           const uint32_t nib = (mw >> bshift) & 0xFu;
           bv[jj] = make_float4((nib & 1u) ? 1.0f : 0.0f, (nib & 2u) ? 1.0f : 0.0f, (nib & 4u) ? 1.0f : 0.0f,
                                (nib & 8u) ? 1.0f : 0.0f);
@@ -442,6 +447,7 @@ spmm_tc_kernel(PlanView pv, const float* __restrict__ x /* tf32-rounded, 16B ali
             const uint32_t w0 = static_cast<uint32_t>(m4.x), w1 = static_cast<uint32_t>(m4.y),
                            w2 = static_cast<uint32_t>(m4.z), w3 = static_cast<uint32_t>(m4.w);
             const uint32_t mine = bword == 0 ? w0 : (bword == 1 ? w1 : (bword == 2 ? w2 : w3));
+            ring_dep |= (w0 | w1 | w2 | w3) >> 1;
             nibs[jj] = (mine >> bshift) & 0xFu;
             // rank of the first of my four bits among the tile's set bits (bit order r*8+c)
             ranks[jj] = __popc(mine & ((1u << bshift) - 1u)) + (bword > 0 ? __popc(w0) : 0) +
@@ -474,11 +480,12 @@ spmm_tc_kernel(PlanView pv, const float* __restrict__ x /* tf32-rounded, 16B ali
         last = (tf & kTileLast) != 0 || (g0 + lane == sl.t1 - 1);
       }
       const uint32_t fm = __ballot_sync(0xffffffffu, first), lm = __ballot_sync(0xffffffffu, last);
+      ring_dep |= fm | lm;
       // publish the oldest own stage once its copies have landed -- BEFORE blocking on a free slot, so a
       // landed stage never waits for the MMAs of an older one
       if (trp) trace_put(trace, 1, k / kProducers, 2);
-      if (k - published >= OWN_LAG * kProducers) {
-        cp_async_wait_group<OWN_LAG - 1>();
+      if (OWN_LAG > 0 && k - published >= OWN_LAG * kProducers) {
+        cp_async_wait_group<(OWN_LAG > 0 ? OWN_LAG - 1 : 0)>();
         if (trp) trace_put(trace, 1, k / kProducers, 3);
         fence_proxy_async_smem();
         __syncwarp();
@@ -496,6 +503,7 @@ spmm_tc_kernel(PlanView pv, const float* __restrict__ x /* tf32-rounded, 16B ali
             const uint32_t a_tile = a_smem + s * C::kAStageBytes + j * C::kATileBytes;
             const int4 c0 = lds_v4(meta + j * 64), c1 = lds_v4(meta + j * 64 + 16);   // rows to gather (-1: padding)
             const int32_t cols[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+            ring_dep |= static_cast<uint32_t>(c0.x | c0.y | c0.z | c0.w | c1.x | c1.y | c1.z | c1.w);
             if (nvec == DBLK * 32) {
               // full-width rows: lane -> vector `lane` (+32) of each of the 8 gathered rows
 #pragma unroll
@@ -534,12 +542,19 @@ spmm_tc_kernel(PlanView pv, const float* __restrict__ x /* tf32-rounded, 16B ali
       if (trp) trace_put(trace, 1, k / kProducers, 6);
       __syncwarp();
       if (lane == 0) {
-        mbar_arrive(meta_empty + 8 * ms);             // every lane of this warp has read the records
+        mbar_arrive_after_loads(meta_empty + 8 * ms, ring_dep);   // every lane of this warp HAS the records in registers
         if (member == 0) sts_u32(info_smem + 4 * s, fm | (lm << 8) | (static_cast<uint32_t>(nt) << 16));
       }
 #pragma unroll
       for (int jj = 0; jj < kTpm; ++jj)
         if (j_lo + jj < nt) sts_v4(b_smem + s * C::kBStageBytes + (j_lo + jj) * kBTileBytes + lane * 16, bv[jj]);
+      if (OWN_LAG == 0) {
+        cp_async_wait_all();
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(full + 8 * s);
+        published += kProducers;
+      }
       if (trp) trace_put(trace, 1, k / kProducers, 7);
     }
     // drain: publish the own stages still in flight
@@ -649,21 +664,42 @@ cudaError_t launch_pass(const tcgnn_plan* plan, const PlanView& pv, int grid, co
     count_launch();
   }
   constexpr int T = 8 / DBLK;   // tiles in 32 KB of A
-  // TCGNN_SPMM_TEAM=1 keeps one gathering warp per stage (the round-1 shape; a tuning knob, results are identical)
-  static const int team = [] {
+  // Gathering warps per stage and publication lag (tuning knobs TCGNN_SPMM_TEAM / TCGNN_SPMM_LAG; results are
+  // identical).  Measured on B200 (profiles/r02d_spmm_team_lag_ab.txt): the weighted kernel gains 1.25-1.4x from a
+  // second warp per stage (its B tiles cost a load and four shuffles per lane and tile), the D = 256 kernels 3 %,
+  // the unweighted D <= 128 kernel loses 2-3 % to the extra warps; publishing right after landing (lag 0) is worth
+  // 1-5 % except for the weighted D = 256 kernel.
+  const bool weighted = wperm != nullptr;
+  static const int team_env = [] {
     const char* e = getenv("TCGNN_SPMM_TEAM");
-    return e != nullptr && atoi(e) == 1 ? 1 : 2;
+    return e != nullptr ? atoi(e) : 0;
   }();
-#define TCGNN_LAUNCH(G, S, P, STAGED)                                                                              \
-  return team == 1 ? launch_kernel<Cfg<DBLK, G, S, P, 1, STAGED, 1>, DBLK>(plan, pv, grid, xr, ldr, wperm, y, ldy, dim, \
-                                                                         mode_flags, stream)                        \
-                   : launch_kernel<Cfg<DBLK, G, S, P, 1, STAGED, 2>, DBLK>(plan, pv, grid, xr, ldr, wperm, y, ldy, dim, \
-                                                                         mode_flags, stream)
+  static const int lag_env = [] {
+    const char* e = getenv("TCGNN_SPMM_LAG");
+    return e != nullptr ? atoi(e) : -1;
+  }();
+  const int team = team_env == 1 || team_env == 2 ? team_env : ((weighted || DBLK == 2) ? 2 : 1);
+  const int lag = lag_env == 0 || lag_env == 1 ? lag_env : ((weighted && DBLK == 2) ? 1 : 0);
+#define TCGNN_LAUNCH_TL(G, S, P, STAGED, TEAM, LAG) \
+  launch_kernel<Cfg<DBLK, G, S, P, LAG, STAGED, TEAM>, DBLK>(plan, pv, grid, xr, ldr, wperm, y, ldy, dim, mode_flags, stream)
+#define TCGNN_LAUNCH(G, S, P, STAGED)                                                          \
+  return team == 1 ? (lag == 1 ? TCGNN_LAUNCH_TL(G, S, P, STAGED, 1, 1) : TCGNN_LAUNCH_TL(G, S, P, STAGED, 1, 0)) \
+                   : (lag == 1 ? TCGNN_LAUNCH_TL(G, S, P, STAGED, 2, 1) : TCGNN_LAUNCH_TL(G, S, P, STAGED, 2, 0))
   // Dense windows (hundreds of tiles each: reddit): the deepest ring, output written straight from registers
   // (rare).  Sparse windows: one output tile every few tiles -- stage it and hand it to the TMA engine; the
   // staging buffers cost one pipeline slot.
   int preset = preset_setting();
   if (preset == 0) preset = static_cast<int64_t>(plan->num_tiles) >= 256LL * plan->num_windows ? 1 : 2;
+  // TCGNN_SPMM_SHAPE=1 (tuning knob): half-size stages, twice as many of them, one gathering warp each -- the same
+  // bytes in flight, recycled at twice the granularity
+  static const int shape = [] {
+    const char* e = getenv("TCGNN_SPMM_SHAPE");
+    return e != nullptr ? atoi(e) : 0;
+  }();
+  if (shape == 1) {
+    if (preset == 1) return lag == 1 ? TCGNN_LAUNCH_TL(T / 2, 12, 12, false, 1, 1) : TCGNN_LAUNCH_TL(T / 2, 12, 12, false, 1, 0);
+    return lag == 1 ? TCGNN_LAUNCH_TL(T / 2, 10, 10, true, 1, 1) : TCGNN_LAUNCH_TL(T / 2, 10, 10, true, 1, 0);
+  }
   switch (preset) {
     case 1: TCGNN_LAUNCH(T, 6, 6, false);
 #ifdef TCGNN_DEBUG_SWITCHES
@@ -673,6 +709,7 @@ cudaError_t launch_pass(const tcgnn_plan* plan, const PlanView& pv, int grid, co
     default: TCGNN_LAUNCH(T, 5, 5, true);
   }
 #undef TCGNN_LAUNCH
+#undef TCGNN_LAUNCH_TL
 }
 
 }  // namespace

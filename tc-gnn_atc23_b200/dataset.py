@@ -10,6 +10,11 @@
     falls back to the synthetic workload `<name>` / `<name>-like` when there is one.
 CSR is built exactly as the reference does (scipy coo -> csr: duplicates merged, columns sorted,
 int32), features are standard normal, labels all ones (reference dataset.py:115,122).
+
+`reorder="hub" | "minhash" | "degree"` relabels the nodes once (reorder.py: symmetric relabelling that packs rows
+with overlapping neighbour sets into the same 16-row windows, i.e. fewer TC blocks for the same graph) -- what the
+reference's never-set `reorder_flag` (dataset.py:24) stands for.  `self.perm[new_id] = old_id`; features and labels
+are generated for the relabelled ids (the reference's are random / constant, so nothing else has to move).
 """
 from __future__ import annotations
 
@@ -28,7 +33,7 @@ def _device():
 
 
 class TCGNN_dataset(torch.nn.Module):
-    def __init__(self, path, dim, num_class, load_from_txt=True, verbose=False, seed=None):
+    def __init__(self, path, dim, num_class, load_from_txt=True, verbose=False, seed=None, reorder=None):
         super().__init__()
         self.nodes = set()
         self.load_from_txt = load_from_txt
@@ -37,7 +42,10 @@ class TCGNN_dataset(torch.nn.Module):
         self.num_features = dim
         self.num_classes = num_class
         self.edge_index = None
-        self.reorder_flag = False
+        self.reorder_flag = reorder not in (None, "none", False)
+        self.reorder_method = reorder if self.reorder_flag else None
+        self.reorder_report = None
+        self.perm = None
         self.verbose_flag = verbose
         self.avg_degree = -1
         self.avg_edgeSpan = -1
@@ -109,11 +117,24 @@ class TCGNN_dataset(torch.nn.Module):
             csr.sort_indices()
             if self.verbose_flag:
                 print("# Build CSR (s): {:.3f}".format(time.perf_counter() - t0))
-            # NB like the reference, num_edges keeps the raw pair count while the CSR may be shorter
-            # after duplicate merging; operators size everything from column_index.
+            # Unlike the reference (which keeps the raw pair count, dataset.py:79), num_edges is the number of
+            # STORED non-zeros after scipy merged duplicate pairs: it is what callers size edgeToColumn /
+            # edgeToRow with, and the operators read exactly len(column_index) entries (longer arrays are accepted).
             self.column_index = torch.from_numpy(csr.indices.astype(np.int32))
             self.row_pointers = torch.from_numpy(csr.indptr.astype(np.int32))
             self.num_edges = int(self.column_index.numel())
+        if self.reorder_flag and self.num_edges > 0:
+            import reorder as _reorder
+            t0 = time.perf_counter()
+            dev = _device()
+            rp, ci, perm, rep = _reorder.reorder_graph(self.row_pointers.to(dev), self.column_index.to(dev),
+                                                       self.reorder_method)
+            self.row_pointers, self.column_index, self.perm = rp.cpu(), ci.cpu(), perm.cpu()
+            self.reorder_report = rep
+            if self.verbose_flag:
+                print("# Reorder ({}) (s): {:.3f}  TC blocks {} -> {} ({:.1f} %)".format(
+                    self.reorder_method, time.perf_counter() - t0, rep["tc_blocks_before"], rep["tc_blocks_after"],
+                    rep["reduction_pct"]))
         if self.verbose_flag:
             print("# nodes: {}".format(self.num_nodes))
             print("# avg_degree: {:.2f}".format(self.avg_degree))

@@ -99,3 +99,42 @@ def test_reference_python_layer_binds_to_our_module():
     i = torch.zeros(5, dtype=torch.int32)
     with pytest.raises(RuntimeError):
         TCGNN.forward(x, i, i, i, i, i)
+
+
+def test_reordering_is_an_isomorphism_and_never_needs_more_blocks_on_skewed_graphs():
+    """reorder.py: the relabelled CSR is P A P^T (same edge multiset under the permutation, rows sorted), SpMM
+    commutes with it (oracle), and on an R-MAT graph every order needs fewer TC blocks than the natural one; the
+    block counter agrees with the SGT oracle's blockPartition sum."""
+    import reorder
+    import tcgnn_oracle as orc
+    n = 6000
+    rp, ci = orc.rmat_graph(n, 200000, seed=3)
+    t_rp, t_ci = torch.from_numpy(rp), torch.from_numpy(ci)
+    bp, _, _, _ = orc.sgt(rp, ci, n)
+    base = reorder.count_tc_blocks(t_rp, t_ci)
+    assert base == int(bp.sum())
+    assert reorder.naive_tc_blocks(t_rp, t_ci) >= base
+    x = np.random.default_rng(0).integers(-3, 4, size=(n, 8)).astype(np.float32)
+    y = orc.spmm(x, rp, ci)
+    for method in ("degree", "minhash", "hub"):
+        rp2, ci2, perm, rep = reorder.reorder_graph(t_rp, t_ci, method)
+        p = perm.numpy()
+        assert sorted(p.tolist()) == list(range(n))
+        assert rep["tc_blocks_before"] == base and rep["tc_blocks_after"] < base
+        assert rep["tc_blocks_after"] == int(orc.sgt(rp2.numpy(), ci2.numpy(), n)[0].sum())
+        # rows of the relabelled graph are sorted and duplicate-free, like scipy's CSR
+        r2, c2 = rp2.numpy(), ci2.numpy()
+        rows2 = np.repeat(np.arange(n), np.diff(r2))
+        assert np.all((np.diff(c2) > 0) | (np.diff(rows2) > 0))
+        # (P A P^T)(P x) = P (A x)
+        assert np.array_equal(orc.spmm(x[p], r2, c2), y[p])
+
+
+def test_dataset_reorder_option(tmp_path):
+    from dataset import TCGNN_dataset
+    ds0 = TCGNN_dataset("rmat:3000:60000:1", 8, 3, load_from_txt=False, seed=1)
+    ds1 = TCGNN_dataset("rmat:3000:60000:1", 8, 3, load_from_txt=False, seed=1, reorder="hub")
+    assert ds0.perm is None and ds0.reorder_report is None and not ds0.reorder_flag
+    assert ds1.reorder_flag and ds1.perm.numel() == 3000
+    assert ds1.column_index.numel() == ds0.column_index.numel()
+    assert ds1.reorder_report["tc_blocks_after"] <= ds1.reorder_report["tc_blocks_before"]

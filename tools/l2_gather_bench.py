@@ -30,17 +30,24 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "l2_gather"))
+    ap.add_argument("--from-jsonl", default=None, help="re-derive <out>_peak.json from a kept sweep (no GPU needed)")
     args = ap.parse_args()
-    build()
-    res = subprocess.run([BIN] + (["--quick"] if args.quick else []), stdout=subprocess.PIPE, text=True, timeout=1500)
-    lines = [json.loads(ln) for ln in res.stdout.splitlines() if ln.startswith("{")]
-    os.makedirs(os.path.dirname(args.out), exist_ok=True)
-    with open(args.out + ".jsonl", "w") as fh:
-        for ln in lines:
-            fh.write(json.dumps(ln) + "\n")
+    if args.from_jsonl:
+        with open(args.from_jsonl) as fh:
+            lines = [json.loads(ln) for ln in fh if ln.startswith("{")]
+        rc = 0
+    else:
+        build()
+        res = subprocess.run([BIN] + (["--quick"] if args.quick else []), stdout=subprocess.PIPE, text=True, timeout=1500)
+        rc = res.returncode
+        lines = [json.loads(ln) for ln in res.stdout.splitlines() if ln.startswith("{")]
+        os.makedirs(os.path.dirname(args.out), exist_ok=True)
+        with open(args.out + ".jsonl", "w") as fh:
+            for ln in lines:
+                fh.write(json.dumps(ln) + "\n")
     runs = [ln for ln in lines if "mode" in ln]
-    if res.returncode != 0 or not runs:
-        print(f"l2_gather_bench failed (rc={res.returncode}); {len(runs)} lines kept", file=sys.stderr)
+    if rc != 0 or not runs:
+        print(f"l2_gather_bench failed (rc={rc}); {len(runs)} lines kept", file=sys.stderr)
         return 1
 
     def best(mode, lo, hi):
@@ -53,7 +60,11 @@ def main():
             "reddit_sized": best("ldgsts", 110, 130), "beyond_l2": best("ldgsts", 400, 1e9),
             "gather4": {"resident": best("gather4", 0, 64), "reddit_sized": best("gather4", 110, 130)},
             "gather4_wide": {"resident": best("gather4_wide", 0, 64), "reddit_sized": best("gather4_wide", 110, 130)},
-            "checks": [ln for ln in lines if "check" in ln]}
+            "checks": [ln for ln in lines if "check" in ln],
+            # best ldgsts figure per working-set size: the ceiling for a feature matrix of that size
+            "curve": [{"working_set_mb": ws, "bytes_per_clk": best("ldgsts", ws - 0.01, ws + 0.01)["bytes_per_clk"],
+                       "gbs": best("ldgsts", ws - 0.01, ws + 0.01)["gbs"]}
+                      for ws in sorted({r["working_set_mb"] for r in runs if r["mode"] == "ldgsts"})]}
     with open(args.out + "_peak.json", "w") as fh:
         json.dump(peak, fh, indent=1)
     print(json.dumps({k: peak[k] for k in ("bytes_per_clk", "gbs")}))
