@@ -495,6 +495,14 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    # stdout carries exactly ONE JSON line: everything else that writes to file descriptor 1 (NCCL's version banner,
+    # printf from native code) is sent to stderr, the line itself goes to the saved descriptor at the end
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        os.write(json_fd, (json.dumps(obj) + "\n").encode())
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -514,7 +522,7 @@ def main():
     dev = torch.device("cuda", local_rank) if torch.cuda.is_available() else torch.device("cpu")
 
     if args.impl != "ours":
-        return reference_arm(args, n, target_nnz, dim, kind, dev)
+        return reference_arm(args, n, target_nnz, dim, kind, dev, emit)
 
     import torch.distributed as dist
     if world > 1:
@@ -698,14 +706,14 @@ def main():
                 variants[vname] = {"failed": repr(exc)}
         result["variants"] = variants
     if rank == 0:
-        print(json.dumps(result), flush=True)
+        emit(result)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     return 0
 
 
-def reference_arm(args, n, target_nnz, dim, kind, dev):
+def reference_arm(args, n, target_nnz, dim, kind, dev, emit):
     import graphgen
     rp, ci = graphgen.synthetic_graph(n, target_nnz, kind=kind, seed=args.seed, device=dev)
     nnz = int(ci.numel())
@@ -722,7 +730,7 @@ def reference_arm(args, n, target_nnz, dim, kind, dev):
     if ref is None or args.op != "spmm" or dim > 128 or dim % 16 != 0:
         # CPU port: K passes over a bounded sample, all host cores
         if cpu is None:
-            print(json.dumps({"impl": "reference", "unavailable": "reference kernels cover only SpMM D<=128, D%16==0 "
+            emit(({"impl": "reference", "unavailable": "reference kernels cover only SpMM D<=128, D%16==0 "
                               "and the CPU port covers SpMM"}))
             return 0
         vals = [cpu_spmm_baseline(rp_h, ci_h, x_h, dim, budget_s=4.0)["value"] for _ in range(max(1, min(args.steps, 3)))]
@@ -731,7 +739,7 @@ def reference_arm(args, n, target_nnz, dim, kind, dev):
         common.update({"value": v, "ms_per_step": round(nnz / v * 1e3, 3), "cpu_baseline": cpu,
                        "dtype": "tf32", "dtype_note": "fp32 arithmetic on tf32-rounded operands", "reference_device": "cpu",
                        "e2e": {"value": v, "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
-        print(json.dumps(common), flush=True)
+        emit(common)
         return 0
     # reference CUDA kernels on this GPU
     sgt = [torch.zeros((n + 15) // 16 + 1, dtype=torch.int32), torch.zeros(nnz, dtype=torch.int32),
@@ -791,7 +799,7 @@ def reference_arm(args, n, target_nnz, dim, kind, dev):
         "clocks": clocks, "prep": {"reference_sgt_cpu_s": round(t_prep, 3)},
         "cpu_baseline": cpu if cpu is not None else {"value": None, "unit": "edges/s", "cores": 0, "kind": "port",
                                                      "sample": "skipped"}})
-    print(json.dumps(common), flush=True)
+    emit(common)
     return 0
 
 
