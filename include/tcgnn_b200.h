@@ -175,6 +175,10 @@ int tcgnn_gather_rows(const float* src, int64_t ld, const int32_t* rows, int64_t
  * (int32)(*flag - value) >= 0.  `flag` is device memory a peer GPU's copy engine writes after its rows have landed.
  * timeout_ms > 0: gives up after that long and sets *error_out (device int32, nullable) to 1 instead of hanging. */
 int tcgnn_stream_wait_flag(const int32_t* flag, int32_t value, int32_t timeout_ms, int32_t* error_out, void* stream);
+/* Same, the expected value read from device memory when the wait executes (a step counter the caller bumps on the
+ * device): the launch is identical every step, so the whole exchange step can be replayed as a CUDA graph. */
+int tcgnn_stream_wait_flag_dev(const int32_t* flag, const int32_t* value_dev, int32_t timeout_ms, int32_t* error_out,
+                               void* stream);
 
 /* SpMM with HOST feature / result buffers (the end-to-end path of a caller whose features live in host memory;
  * page-locked buffers for full PCIe speed).  x_host: [num_cols, ldx], y_host: [num_nodes, ldy] in host memory;

@@ -669,6 +669,23 @@ void stream_wait_flag(torch::Tensor flags, int64_t index, int64_t value, int64_t
                "tcgnn_stream_wait_flag");
 }
 
+void stream_wait_flag_dev(torch::Tensor flags, int64_t index, torch::Tensor value_dev, int64_t timeout_ms,
+                          torch::Tensor error_out) {
+  CHECK_INPUT(flags);
+  CHECK_I32(flags);
+  CHECK_INPUT(value_dev);
+  CHECK_I32(value_dev);
+  CHECK_INPUT(error_out);
+  CHECK_I32(error_out);
+  TORCH_CHECK(index >= 0 && index < flags.numel() && value_dev.numel() >= 1 && error_out.numel() >= 1,
+              "stream_wait_flag_dev: bad arguments");
+  c10::cuda::CUDAGuard guard(flags.device());
+  auto stream = c10::cuda::getCurrentCUDAStream(flags.get_device()).stream();
+  check_status(tcgnn_stream_wait_flag_dev(flags.data_ptr<int32_t>() + index, value_dev.data_ptr<int32_t>(),
+                                          static_cast<int32_t>(timeout_ms), error_out.data_ptr<int32_t>(), stream),
+               "tcgnn_stream_wait_flag_dev");
+}
+
 // (row_ptr_t, col_idx_t, edge_map_t) of A^T on the device (tcgnn_csr_transpose)
 std::vector<torch::Tensor> csr_transpose(torch::Tensor nodePointer, torch::Tensor edgeList, int64_t num_cols) {
   CHECK_INPUT(nodePointer);
@@ -765,6 +782,9 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("csr_transpose", &csr_transpose, "(nodePointer, edgeList, num_cols=-1) -> [row_ptr_t, col_idx_t, edge_map_t]",
         py::arg("nodePointer"), py::arg("edgeList"), py::arg("num_cols") = -1);
   m.def("gather_rows", &gather_rows, "(src [n, d], rows int32 [m], dst [>= m, d]): dst[i] = src[rows[i]]");
+  m.def("stream_wait_flag_dev", &stream_wait_flag_dev,
+        "(flags int32, index, value_dev int32[1], timeout_ms, error_out int32[1]): like stream_wait_flag, the expected "
+        "value read from device memory when the wait executes (CUDA-graph friendly)");
   m.def("stream_wait_flag", &stream_wait_flag,
         "(flags int32, index, value, timeout_ms, error_out int32[1]): block the current stream until flags[index] >= value");
   m.def("push_rows", &push_rows, "(local, peer_ptrs, seg_begin_rows, seg_end_rows): copy row segments to peers");

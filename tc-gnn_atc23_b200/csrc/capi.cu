@@ -235,7 +235,17 @@ int tcgnn_stream_wait_flag(const int32_t* flag, int32_t value, int32_t timeout_m
     set_last_error("tcgnn_stream_wait_flag: flag is null or misaligned");
     return TCGNN_ERR_INVALID_ARG;
   }
-  return wait_flag_launch(flag, value, timeout_ms, error_out, static_cast<cudaStream_t>(stream));
+  return wait_flag_launch(flag, value, nullptr, timeout_ms, error_out, static_cast<cudaStream_t>(stream));
+}
+
+int tcgnn_stream_wait_flag_dev(const int32_t* flag, const int32_t* value_dev, int32_t timeout_ms, int32_t* error_out,
+                               void* stream) {
+  if (flag == nullptr || value_dev == nullptr || (reinterpret_cast<uintptr_t>(flag) & 3) != 0 ||
+      (reinterpret_cast<uintptr_t>(value_dev) & 3) != 0) {
+    set_last_error("tcgnn_stream_wait_flag_dev: flag / value_dev is null or misaligned");
+    return TCGNN_ERR_INVALID_ARG;
+  }
+  return wait_flag_launch(flag, 0, value_dev, timeout_ms, error_out, static_cast<cudaStream_t>(stream));
 }
 
 int tcgnn_sddmm_f32_ex(tcgnn_plan* plan, const float* x, int64_t ldx, float* edge_out, int32_t dim, uint32_t flags,

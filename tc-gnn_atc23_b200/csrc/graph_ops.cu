@@ -112,7 +112,11 @@ gather_rows_kernel(const float4* __restrict__ src, int64_t ldv, const int32_t* _
   }
 }
 
-__global__ void wait_flag_kernel(const int32_t* flag, int32_t value, unsigned long long timeout_ns, int32_t* error_out) {
+// value_dev != nullptr: the expected value is read from device memory when the kernel runs (a step counter the
+// caller bumps on the device), so the launch is the same every step and can live in a CUDA graph
+__global__ void wait_flag_kernel(const int32_t* flag, int32_t value, const int32_t* value_dev,
+                                 unsigned long long timeout_ns, int32_t* error_out) {
+  if (value_dev != nullptr) value = *value_dev;
   const uint64_t t0 = global_timer_ns();
   for (;;) {
     int32_t v;
@@ -244,8 +248,10 @@ int gather_rows_launch(const float* src, int64_t ld, const int32_t* rows, int64_
   return TCGNN_OK;
 }
 
-int wait_flag_launch(const int32_t* flag, int32_t value, int32_t timeout_ms, int32_t* error_out, cudaStream_t stream) {
-  wait_flag_kernel<<<1, 1, 0, stream>>>(flag, value, timeout_ms > 0 ? static_cast<unsigned long long>(timeout_ms) * 1000000ULL : 0ULL,
+int wait_flag_launch(const int32_t* flag, int32_t value, const int32_t* value_dev, int32_t timeout_ms,
+                     int32_t* error_out, cudaStream_t stream) {
+  wait_flag_kernel<<<1, 1, 0, stream>>>(flag, value, value_dev,
+                                        timeout_ms > 0 ? static_cast<unsigned long long>(timeout_ms) * 1000000ULL : 0ULL,
                                         error_out);
   count_launch();
   cudaError_t e = cudaGetLastError();

@@ -103,7 +103,8 @@ int csr_transpose_launch(const int32_t* row_ptr, const int32_t* col_idx, int32_t
                          cudaStream_t stream);
 int gather_rows_launch(const float* src, int64_t ld, const int32_t* rows, int64_t n_rows, float* dst,
                        cudaStream_t stream);
-int wait_flag_launch(const int32_t* flag, int32_t value, int32_t timeout_ms, int32_t* error_out, cudaStream_t stream);
+int wait_flag_launch(const int32_t* flag, int32_t value, const int32_t* value_dev, int32_t timeout_ms,
+                     int32_t* error_out, cudaStream_t stream);
 enum HostOp { kHostSpmm = 0, kHostSddmm = 1, kHostAgnn = 2 };
 int host_op_launch(tcgnn_plan* plan, int op, const float* x_host, int64_t ldx, const float* dev_arg, float* y_host,
                    int64_t ldy, float* e_host, int32_t dim, cudaStream_t stream);

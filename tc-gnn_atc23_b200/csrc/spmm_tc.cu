@@ -690,9 +690,8 @@ cudaError_t launch_pass(const tcgnn_plan* plan, const PlanView& pv, int grid, co
   // staging buffers cost one pipeline slot.
   int preset = preset_setting();
   if (preset == 0) preset = static_cast<int64_t>(plan->num_tiles) >= 256LL * plan->num_windows ? 1 : 2;
-  // Y += ...: every window is combined, so the staged epilogue (one bulk reduce-add per window) always pays -- the
-  // register epilogue would issue 16 scalar atomics per thread and window
-  if ((mode_flags & kFlagAccumulate) && preset == 1) preset = 2;
+  // (Y += ... keeps this choice: with >= 256 tiles per window the 16 scalar atomics per thread and window of the
+  // register epilogue cost ~3 % while the staged shape gives up a pipeline stage -- measured on 2 GPUs, r02g)
   // TCGNN_SPMM_SHAPE=1 (tuning knob): half-size stages, twice as many of them, one gathering warp each -- the same
   // bytes in flight, recycled at twice the granularity
   static const int shape = [] {

@@ -144,8 +144,8 @@ def _all_ranks_ok(ok: bool, device, group) -> bool:
 
 
 class OverlapState:
-    """Buffers of the overlapped exchange for one feature width (see RowPanel.aggregate_overlapped)."""
-    EPOCH_RING = 1 << 20   # flag values are read from a device-resident ramp by the copy engine
+    """Buffers, step counter and captured graphs of the overlapped exchange for one feature width
+    (see RowPanel.aggregate_overlapped)."""
 
 
 class RowPanel:
@@ -473,11 +473,11 @@ class RowPanel:
         st.stage = [torch.empty((int(need[q, me]), d), dtype=torch.float32, device=device)
                     if (q != me and lists[q].numel() > 0) else None for q in range(w)]
         st.xr = [torch.empty((self.num_rows, d), dtype=torch.float32, device=device) for _ in range(2)]
-        st.vals = torch.arange(OverlapState.EPOCH_RING, dtype=torch.int32, device=device)
+        st.step_dev = torch.zeros(1, dtype=torch.int32, device=device)   # step number; flag writes copy it
         st.err = torch.zeros(1, dtype=torch.int32, device=device)
         st.copy_stream = torch.cuda.Stream(device=device)
-        st.ev_round = [torch.cuda.Event() for _ in range(2)]
-        st.epoch = 0
+        st.steps = 0
+        st.graphs = {}
         torch.cuda.synchronize(device)
         st.flags_hdl.barrier(channel=0)                    # flags are zeroed everywhere before anybody pushes
         self._ovl[d] = st
@@ -490,46 +490,77 @@ class RowPanel:
         meanwhile its SMs compute the own-panel product, then -- in the order the pushes of the other ranks arrive
         -- one TCGNN_ACCUMULATE product per source panel, each behind a stream-ordered wait on that source's flag.
         No barrier: the receive area is double-buffered by step parity, and a rank's pushes of step k + 1 are
-        ordered after its own kernels of step k, which needed everybody's data of step k."""
-        import TCGNN
+        ordered after its own kernels of step k, which needed everybody's data of step k.
+
+        The step is a fixed sequence of ~30 small launches and copies (at 8 GPUs the kernels of a reddit-sized step
+        take 0.4 ms, issuing them from Python 0.9 ms), so after two eager steps it is captured once per step parity
+        and input buffer as a CUDA graph and replayed (TCGNN_EXCHANGE_GRAPH=0 keeps it eager).  Nothing in it
+        depends on host-side state: the step number lives in device memory (bumped inside the step), the flag
+        writes copy it, the waits compare against it."""
         d = x_local.shape[1]
         st = self._ovl[d]
+        if self.num_rows == 0 and self.world_size == 1:
+            return x_local.new_zeros((0, d))
+        st.steps += 1
+        b = st.steps & 1
+        x_local = x_local.contiguous()
+        if os.environ.get("TCGNN_EXCHANGE_GRAPH", "1") == "0" or st.steps <= 2:
+            return self._overlap_step(x_local, st, b)
+        key = (x_local.data_ptr(), tuple(x_local.shape), b)
+        g = st.graphs.get(key)
+        if g is None:
+            if len(st.graphs) >= 16:          # inputs that keep moving: stay eager instead of capturing forever
+                return self._overlap_step(x_local, st, b)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, capture_error_mode="thread_local"):
+                out = self._overlap_step(x_local, st, b)
+            g = st.graphs[key] = (graph, out, x_local)   # x_local kept alive: its address is baked into the graph
+        g[0].replay()
+        return g[1].clone()
+
+    def _overlap_step(self, x_local: torch.Tensor, st, b: int) -> torch.Tensor:
+        """The step itself (eager or under stream capture): forks the copy stream off the current one, joins it."""
+        import TCGNN
+        d = x_local.shape[1]
         subs = self._sub
         w, me = self.world_size, self.rank
-        st.epoch += 1
-        if st.epoch >= OverlapState.EPOCH_RING - 1:
-            raise RuntimeError("overlapped exchange: step counter exhausted; call reset_overlap()")
-        epoch, b = st.epoch, st.epoch & 1
         cur = torch.cuda.current_stream(x_local.device)
         xr = st.xr[b]
+        st.step_dev.add_(1)                                  # this step's number, on the device
         if self.num_rows > 0:
-            TCGNN.round_tf32_into(x_local.contiguous(), xr.data_ptr(), d, False)
-        st.ev_round[b].record(cur)
-        with torch.cuda.stream(st.copy_stream):
-            st.copy_stream.wait_event(st.ev_round[b])
+            TCGNN.round_tf32_into(x_local, xr.data_ptr(), d, False)
+        cs = st.copy_stream
+        cs.wait_stream(cur)
+        packed = [q for q in ((me + k) % w for k in range(1, w)) if st.lists[q].numel() > 0 and int(st.need[q, me]) > 0]
+        with torch.cuda.stream(cs):
+            # pack first, all destinations: the pack kernels need SMs, which the products below keep busy -- packs
+            # that queue behind them would delay every later push
+            for q in packed:
+                TCGNN.gather_rows(xr, st.lists[q], st.stage[q])
+        if packed:
+            cur.wait_stream(cs)
+        with torch.cuda.stream(cs):
             for k in range(1, w):
                 q = (me + k) % w
                 n = int(st.need[q, me])
                 if n > 0:
-                    if st.lists[q].numel() > 0:
-                        TCGNN.gather_rows(xr, st.lists[q], st.stage[q])
-                        src = st.stage[q]
-                    else:
-                        src = xr
+                    src = st.stage[q] if st.lists[q].numel() > 0 else xr
                     o = int(st.offs[q, me])
                     st.peer_recv[q][b, o:o + n].copy_(src, non_blocking=True)
-                st.peer_flags[q][me:me + 1].copy_(st.vals[epoch:epoch + 1], non_blocking=True)
-        if self.num_rows == 0:
-            return x_local.new_zeros((0, d))
-        y = TCGNN.source_forward(xr, *subs[me]["graph"], x_is_tf32=True)[0]
+                st.peer_flags[q][me:me + 1].copy_(st.step_dev, non_blocking=True)
         timeout_ms = int(os.environ.get("TCGNN_FLAG_TIMEOUT_MS", "20000"))
+        if self.num_rows > 0:
+            y = TCGNN.source_forward(xr, *subs[me]["graph"], x_is_tf32=True)[0]
+        else:
+            y = x_local.new_zeros((0, d))
         for k in range(1, w):
             p = (me - k) % w
-            TCGNN.stream_wait_flag(st.flags, p, epoch, timeout_ms, st.err)
+            TCGNN.stream_wait_flag_dev(st.flags, p, st.step_dev, timeout_ms, st.err)
             n = int(st.need[me, p])
-            if n > 0 and subs[p]["edges"] > 0:
+            if self.num_rows > 0 and n > 0 and subs[p]["edges"] > 0:
                 o = int(st.offs[me, p])
                 TCGNN.source_forward(st.recv[b, o:o + n], *subs[p]["graph"], x_is_tf32=True, accumulate_into=y)
+        cur.wait_stream(cs)                                   # join: the next step bumps the counter the flag copies read
         return y
 
     def overlap_check(self) -> None:

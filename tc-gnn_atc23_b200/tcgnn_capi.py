@@ -58,6 +58,8 @@ def lib() -> C.CDLL:
         L.tcgnn_csr_transpose.argtypes = [vp, vp, i32, i32, i64, vp, vp, vp, vp]
         L.tcgnn_gather_rows.argtypes = [vp, i64, vp, i64, vp, vp]
         L.tcgnn_stream_wait_flag.argtypes = [vp, i32, i32, vp, vp]
+        L.tcgnn_stream_wait_flag_dev.argtypes = [vp, vp, i32, vp, vp]
+        L.tcgnn_stream_wait_flag_dev.restype = C.c_int
         L.tcgnn_sddmm_f32_host.argtypes = [vp, vp, i64, vp, i32, vp]
         L.tcgnn_agnn_f32_host.argtypes = [vp, vp, i64, vp, vp, i64, vp, i32, vp]
         for name in ("tcgnn_agnn_f32", "tcgnn_csr_transpose", "tcgnn_gather_rows", "tcgnn_stream_wait_flag",
