@@ -8,7 +8,11 @@ Everything is compiled for sm_100a only (`-gencode arch=compute_100a,code=sm_100
 nvcc cross-compiles without a GPU.  Outputs stay inside this directory so they travel to the
 GPU box with the repository snapshot.  Re-runs only rebuild what is out of date.
 
-    python tc-gnn_atc23_b200/build.py [--force] [--no-binding] [--verbose]
+    python tc-gnn_atc23_b200/build.py [--force] [--no-binding] [--verbose] [--debug-switches]
+
+`--debug-switches` compiles the profiling switches in (-DTCGNN_DEBUG_SWITCHES: TCGNN_ABLATE / TCGNN_TRACE /
+TCGNN_PRESET, used by tools/trace.py); the production library does not contain them -- some of them produce wrong
+results on purpose.  Switching between the two kinds of build needs --force.
 """
 from __future__ import annotations
 
@@ -68,8 +72,9 @@ def module_path() -> str:
     return os.path.join(HERE, "TCGNN" + ext_suffix())
 
 
-def build_library(force: bool = False, verbose: bool = False) -> str:
+def build_library(force: bool = False, verbose: bool = False, debug_switches: bool = False) -> str:
     os.makedirs(OBJ, exist_ok=True)
+    extra = ["-DTCGNN_DEBUG_SWITCHES"] if debug_switches else []
     headers = [h if os.path.isabs(h) else os.path.join(CSRC, h) for h in HEADERS]
     jobs = []
     objects = []
@@ -80,7 +85,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
         if not force and _newer(o, [s] + headers):
             continue
         if src.endswith(".cu"):
-            cmd = [NVCC] + NVCC_FLAGS + ["-c", s, "-o", o]
+            cmd = [NVCC] + NVCC_FLAGS + extra + ["-c", s, "-o", o]
         else:
             cmd = ["g++", "-O3", "-std=c++17", "-fPIC", "-pthread", "-I", INCLUDE, "-c", s, "-o", o]
         jobs.append((src, cmd))
@@ -130,8 +135,9 @@ def main() -> None:
     ap.add_argument("--force", action="store_true")
     ap.add_argument("--no-binding", action="store_true")
     ap.add_argument("--verbose", action="store_true")
+    ap.add_argument("--debug-switches", action="store_true")
     args = ap.parse_args()
-    lib = build_library(args.force, args.verbose)
+    lib = build_library(args.force or args.debug_switches, args.verbose, args.debug_switches)
     print("built", lib)
     if not args.no_binding:
         print("built", build_binding(args.force, args.verbose))
