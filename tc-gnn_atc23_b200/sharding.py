@@ -207,6 +207,7 @@ class RowPanel:
         self._symm = {}    # feature width -> (symmetric buffer, handle, peer views, multicast?)
         self._symm_unavailable = False
         self._sub = None   # per-source-panel sub-graphs (overlapped exchange)
+        self._groups = None  # (group sizes, merged sub-graphs of consecutive arrivals)
         self._ovl = {}     # feature width -> OverlapState
         self._ovl_unavailable = False
 
@@ -430,9 +431,78 @@ class RowPanel:
             if self.num_rows > 0:
                 TCGNN.preprocess_panel(ci32, rp32, self.num_rows, max(n_src, 1), BLK_H, BLK_W, bp, e2c, e2r_s)
             subs.append({"graph": (rp32, ci32, bp, e2c, e2r_s), "n_src": n_src, "ref_rows": ref_rows,
-                         "dense": dense, "edges": int(ci32.numel())})
+                         "dense": dense, "edges": int(ci32.numel()), "rows": e2r[mask], "local": local})
         self._sub = subs
         return subs
+
+    def arrival_order(self, q: Optional[int] = None) -> List[int]:
+        """Sources in the order their pushes reach rank q: every rank pushes to its nearest successor first."""
+        q = self.rank if q is None else q
+        return [(q - k) % self.world_size for k in range(1, self.world_size)]
+
+    def default_groups(self) -> List[int]:
+        """How many consecutive arrivals share one product.  One product per source is the finest overlap, but a short
+        launch pays its start-up, its tail and the sparser-window pipeline shape every time: at 8 GPUs eight products
+        took 0.67 ms for 0.36 ms of kernel work (profiles/r02h_*parallel_products*).  Few groups, later ones larger
+        (they wait longer anyway)."""
+        env = os.environ.get("TCGNN_EXCHANGE_GROUPS")
+        n = self.world_size - 1
+        if env:
+            sizes = [int(v) for v in env.split(",") if v.strip()]
+            if sum(sizes) == n and all(v > 0 for v in sizes):
+                return sizes
+        if n <= 1:
+            return [n] if n else []
+        if n <= 3:
+            return [1, n - 1]
+        a = n // 3
+        return [a, a, n - 2 * a]
+
+    def build_group_subgraphs(self, sizes: Optional[Sequence[int]] = None):
+        """Merge the per-source sub-graphs of consecutive arrivals into one sub-graph per group: its column space is
+        the concatenation of the rows those sources ship, in arrival order -- exactly how they sit in the receive
+        area.  Returns a list of {"sources", "graph", "ncols", "edges"}."""
+        import TCGNN
+        sizes = list(sizes) if sizes is not None else self.default_groups()
+        if self._groups is not None and self._groups[0] == tuple(sizes):
+            return self._groups[1]
+        if self._sub is not None and self._sub and "rows" not in self._sub[0]:
+            self._sub = None                  # the raw edge lists were dropped after an earlier merge: rebuild
+        subs = self.build_source_subgraphs()
+        order = self.arrival_order()
+        groups, i = [], 0
+        nwin = (self.num_rows + BLK_H - 1) // BLK_H
+        for sz in sizes:
+            srcs = order[i:i + sz]
+            i += sz
+            rows, cols, off = [], [], 0
+            for p_ in srcs:
+                sb = subs[p_]
+                rows.append(sb["rows"])
+                cols.append(sb["local"] + off)
+                off += sb["n_src"]
+            ncols = max(off, 1)
+            if len(srcs) == 1:
+                g = subs[srcs[0]]["graph"]
+            else:
+                r = torch.cat(rows) if rows else torch.zeros(0, dtype=torch.int64)
+                c = torch.cat(cols) if cols else torch.zeros(0, dtype=torch.int64)
+                key = torch.sort(r * ncols + c).values
+                r = key // ncols
+                dev = key.device
+                rp = torch.zeros(self.num_rows + 1, dtype=torch.int64, device=dev)
+                torch.cumsum(torch.bincount(r, minlength=self.num_rows), 0, out=rp[1:])
+                rp32 = rp.to(torch.int32).contiguous()
+                ci32 = (key - r * ncols).to(torch.int32).contiguous()
+                bp = torch.zeros(nwin, dtype=torch.int32, device=dev)
+                e2c = torch.zeros(max(ci32.numel(), 1), dtype=torch.int32, device=dev)[:ci32.numel()]
+                e2r_s = torch.zeros(max(ci32.numel(), 1), dtype=torch.int32, device=dev)[:ci32.numel()]
+                if self.num_rows > 0:
+                    TCGNN.preprocess_panel(ci32, rp32, self.num_rows, ncols, BLK_H, BLK_W, bp, e2c, e2r_s)
+                g = (rp32, ci32, bp, e2c, e2r_s)
+            groups.append({"sources": srcs, "graph": g, "ncols": off, "edges": int(g[1].numel())})
+        self._groups = (tuple(sizes), groups)
+        return groups
 
     def _setup_overlap(self, d: int, device, group) -> None:
         import torch.distributed._symmetric_memory as symm_mem
@@ -457,10 +527,21 @@ class RowPanel:
         lists = list(torch.split(recv, cnt_in_l))           # lists[q] = my rows rank q wants (empty: all of them)
         # receive area: the sources' rows back to back in rank order; two copies (step parity) so a fast peer's
         # next push never lands in the rows a slow rank is still reading
-        offs = torch.zeros(w, w + 1, dtype=torch.int64)
-        offs[:, 1:] = torch.cumsum(need, 1)
-        rows_max = int(offs[:, -1].max())
+        # receiver q lays its sources out in ARRIVAL order, so consecutive arrivals form one contiguous block
+        offs = torch.zeros(w, w, dtype=torch.int64)
+        totals = []
+        for q in range(w):
+            o = 0
+            for p_ in self.arrival_order(q):
+                offs[q, p_] = o
+                o += int(need[q, p_])
+            totals.append(o)
+        rows_max = max(totals)
         st = OverlapState()
+        st.groups = self.build_group_subgraphs()
+        for sb in subs:                       # the raw edge lists were only needed for the merge
+            sb.pop("rows", None)
+            sb.pop("local", None)
         st.need, st.offs = need, offs
         st.recv = symm_mem.empty((2, max(rows_max, 1), d), dtype=torch.float32, device=device)
         st.recv_hdl = symm_mem.rendezvous(st.recv, grp)
@@ -551,7 +632,7 @@ class RowPanel:
                 st.peer_flags[q][me:me + 1].copy_(st.step_dev, non_blocking=True)
         timeout_ms = int(os.environ.get("TCGNN_FLAG_TIMEOUT_MS", "20000"))
         # Every product ADDS into a zeroed Y (fp32 reduce-adds commute), so the products are independent of each
-        # other: each source's wait + product sits on its own stream, and the block scheduler fills an SM with the
+        # other: each group of sources' waits + product sit on their own stream, and the block scheduler fills an SM with the
         # next ready product's CTA the moment the previous product's CTA on it retires.  Issued back to back on one
         # stream the eight short launches of an 8-GPU step each paid their own start-up and tail (0.74 ms for 0.36 ms
         # of kernel work, profiles/r02h_*serial_products*).
@@ -561,14 +642,14 @@ class RowPanel:
         branches = st.product_streams
         for s_ in branches:
             s_.wait_stream(cur)
-        for k in range(1, w):
-            p = (me - k) % w
-            with torch.cuda.stream(branches[(k - 1) % len(branches)]):
-                TCGNN.stream_wait_flag_dev(st.flags, p, st.step_dev, timeout_ms, st.err)
-                n = int(st.need[me, p])
-                if self.num_rows > 0 and n > 0 and subs[p]["edges"] > 0:
-                    o = int(st.offs[me, p])
-                    TCGNN.source_forward(st.recv[b, o:o + n], *subs[p]["graph"], x_is_tf32=True, accumulate_into=y)
+        for gi, grp_ in enumerate(st.groups):
+            with torch.cuda.stream(branches[gi % len(branches)]):
+                for p in grp_["sources"]:
+                    TCGNN.stream_wait_flag_dev(st.flags, p, st.step_dev, timeout_ms, st.err)
+                n = grp_["ncols"]
+                if self.num_rows > 0 and n > 0 and grp_["edges"] > 0:
+                    o = int(st.offs[me, grp_["sources"][0]])
+                    TCGNN.source_forward(st.recv[b, o:o + n], *grp_["graph"], x_is_tf32=True, accumulate_into=y)
         for s_ in branches:
             cur.wait_stream(s_)
         cur.wait_stream(cs)                                   # join: the next step bumps the counter the flag copies read

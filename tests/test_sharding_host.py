@@ -239,3 +239,39 @@ def _spmm_rect(xs, rp, ci):
     m = ci.max() + 1 if len(ci) else 1
     np.add.at(y, key // m, xs[key % m])
     return y
+
+
+@pytest.mark.parametrize("world,sizes", [(4, None), (8, None), (8, [1, 1, 1, 1, 1, 1, 1]), (8, [7]), (5, [2, 2])])
+def test_group_subgraphs_follow_the_arrival_order_and_sum_to_the_panel_product(world, sizes):
+    """Consecutive arrivals are merged into one sub-graph whose columns index the concatenation of what those
+    sources ship, in arrival order (the layout of the receive area): own product + group products == panel product."""
+    from sharding import RowPanel
+    n = 3203
+    rp, ci = orc.rmat_graph(n, 60000, seed=71)
+    x = np.random.default_rng(7).integers(-4, 5, size=(n, 4)).astype(np.float32)
+    want = orc.spmm(x, rp, ci)
+    t_rp, t_ci = torch.from_numpy(rp), torch.from_numpy(ci)
+    os.environ["TCGNN_DENSE_FRACTION"] = "0.5"          # a mix of whole-panel and packed sources
+    try:
+        for rank in (0, world - 1, world // 2):
+            p = RowPanel(t_rp, t_ci, rank, world)
+            subs = p.build_source_subgraphs()
+            shipped = {}
+            for src, sb in enumerate(subs):
+                b0, b1 = p.bounds[src], p.bounds[src + 1]
+                shipped[src] = x[b0:b1] if sb["dense"] else x[b0:b1][sb["ref_rows"].numpy()]
+            groups = p.build_group_subgraphs(sizes)
+            order = p.arrival_order()
+            assert [s for g in groups for s in g["sources"]] == order and order[0] == (rank - 1) % world
+            y = _spmm_rect(shipped[rank], subs[rank]["graph"][0].numpy(), subs[rank]["graph"][1].numpy())
+            for g in groups:
+                xs = np.concatenate([shipped[s] for s in g["sources"]]) if g["sources"] else np.zeros((0, 4), np.float32)
+                assert g["ncols"] == len(xs)
+                g_rp, g_ci = g["graph"][0].numpy(), g["graph"][1].numpy()
+                if len(g_ci):
+                    o_bp, o_e2c, o_e2r, _ = orc.sgt(g_rp, g_ci, p.num_rows)
+                    assert np.array_equal(g["graph"][2].numpy(), o_bp) and np.array_equal(g["graph"][3].numpy(), o_e2c)
+                    y += _spmm_rect(xs, g_rp, g_ci)
+            assert np.array_equal(y, want[p.row_base:p.row_base + p.num_rows])
+    finally:
+        os.environ.pop("TCGNN_DENSE_FRACTION", None)
