@@ -323,7 +323,8 @@ class Workload:
             self.x_local = x_full
             self.local_rows, self.local_edges, self.row_base = n, self.nnz, 0
         else:
-            self.panel = RowPanel(self.rp, self.ci, rank, world, device=dev)
+            from sharding import calibrated_panel
+            self.panel = calibrated_panel(self.rp, self.ci, rank, world, self.dim, dev)   # boundaries from measured times
             self.graph = self.panel.graph
             self.row_base = self.panel.row_base
             self.x_local = x_full[self.row_base:self.row_base + self.panel.num_rows].contiguous()
@@ -667,6 +668,8 @@ def main():
     }
     if world > 1 and args.op == "spmm":
         st = wl.panel.overlap_stats(dim)
+        if getattr(wl.panel, "calibration", None):
+            result["partition"] = dict(wl.panel.calibration, bounds=wl.panel.bounds)
         if st is not None:
             result["exchange"] = dict(st, kernel_ms_on_gathered_matrix=round(k_ms, 4),
                                       note="rank 0's figures; kernel_ms = this rank's panel SpMM on an already gathered matrix")

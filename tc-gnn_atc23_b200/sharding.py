@@ -143,6 +143,66 @@ def _all_ranks_ok(ok: bool, device, group) -> bool:
     return bool(int(t.item()) == 1)
 
 
+def calibrated_panel(row_ptr: torch.Tensor, col_idx: torch.Tensor, rank: int, world_size: int, dim: int, device,
+                     group=None) -> "RowPanel":
+    """Row panel whose boundaries come from MEASURED kernel times instead of an assumed cost per window.
+
+    The panels are first cut with the default model (TC blocks + 3 per window, bounded send volume); every rank times
+    the panel SpMM on its cut (a few milliseconds), the ranks exchange (TC blocks, windows, time), fit
+    time = a * blocks + b * windows by least squares, and cut again with window cost b / a.  Round 1's fixed cost
+    left the slowest of 8 panels 1.33x behind the fastest on the reddit-sized R-MAT graph (tail panels hold 10x the
+    windows of the hub panel).  Deterministic across ranks: everybody fits the same gathered numbers."""
+    import numpy as np
+    import TCGNN
+    n = int(row_ptr.numel()) - 1
+    nwin_all = (n + BLK_H - 1) // BLK_H
+    g_bp = torch.zeros(nwin_all, dtype=torch.int32, device=row_ptr.device)
+    g_e2c = torch.zeros(col_idx.numel(), dtype=torch.int32, device=row_ptr.device)
+    g_e2r = torch.zeros(col_idx.numel(), dtype=torch.int32, device=row_ptr.device)
+    TCGNN.preprocess_panel(col_idx.contiguous(), row_ptr.contiguous(), n, n, BLK_H, BLK_W, g_bp, g_e2c, g_e2r)
+    sgt = (g_bp, g_e2c, g_e2r)
+    p0 = RowPanel(row_ptr, col_idx, rank, world_size, device=device, sgt=sgt)
+    if world_size < 2 or os.environ.get("TCGNN_CALIBRATE", "1") == "0" or not row_ptr.is_cuda:
+        return p0
+    x = torch.randn(n, dim, device=device)
+    xr = TCGNN.round_tf32(x) if dim % 4 == 0 else x
+    for _ in range(2):
+        p0.spmm(xr, x_is_tf32=dim % 4 == 0)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(device)
+    ev0.record()
+    for _ in range(4):
+        p0.spmm(xr, x_is_tf32=dim % 4 == 0)
+    ev1.record()
+    torch.cuda.synchronize(device)
+    w0 = p0.row_base // BLK_H
+    nw = (p0.num_rows + BLK_H - 1) // BLK_H
+    mine = torch.tensor([float(torch.clamp(g_bp[w0:w0 + nw], min=1).sum()), float(nw), ev0.elapsed_time(ev1) / 4],
+                        dtype=torch.float64, device=device)
+    allv = [torch.zeros_like(mine) for _ in range(world_size)]
+    dist.all_gather(allv, mine, group=group)
+    m = torch.stack(allv).cpu().numpy()
+    a_mat = m[:, :2]
+    coef, *_ = np.linalg.lstsq(a_mat, m[:, 2], rcond=None)
+    a_, b_ = float(coef[0]), float(coef[1])
+    # the overlapped path runs one product per group of sources plus the own one, and each of them walks all windows
+    n_products = 1 if world_size <= 2 else (2 if world_size <= 4 else world_size)
+    if os.environ.get("TCGNN_CALIBRATE_PRODUCTS"):
+        n_products = int(os.environ["TCGNN_CALIBRATE_PRODUCTS"])
+    wc = 3 if a_ <= 0 else int(round(min(max(b_ / a_ * n_products, 0.0), 64.0)))
+    import TCGNN as _T
+    _T.clear_plan_cache()
+    del x, xr
+    if wc == 3:
+        return p0
+    bounds = partition_rows(row_ptr, world_size, block_partition=g_bp, window_cost=wc,
+                            send_cost_per_row=default_send_cost(world_size))
+    p1 = RowPanel(row_ptr, col_idx, rank, world_size, bounds=bounds, device=device, sgt=sgt)
+    p1.calibration = {"window_cost": wc, "products_per_step": n_products, "fit_ms_per_block": a_, "fit_ms_per_window": b_,
+                      "times_before_ms": [round(float(v), 4) for v in m[:, 2]]}
+    return p1
+
+
 class OverlapState:
     """Buffers, step counter and captured graphs of the overlapped exchange for one feature width
     (see RowPanel.aggregate_overlapped)."""
@@ -370,7 +430,10 @@ class RowPanel:
         all-gather + one panel SpMM."""
         mode = os.environ.get("TCGNN_EXCHANGE", "auto")
         pre = self._can_preround(x_local)
-        if (pre and mode in ("auto", "overlap") and self.world_size > 1 and not self._ovl_unavailable
+        # 2 GPUs: the exchange is 0.15 ms of a 1.8 ms step and splitting the product in two costs more than hiding it
+        # saves (1.83 vs 1.77 ms, profiles/r02h_exchange_probe2_n2.txt); from 3 GPUs on the overlapped path wins
+        want_overlap = mode == "overlap" or (mode == "auto" and self.world_size > 2)
+        if (pre and want_overlap and self.world_size > 1 and not self._ovl_unavailable
                 and dist.get_backend(group) == "nccl"):
             d = x_local.shape[1]
             if d not in self._ovl:
@@ -451,12 +514,11 @@ class RowPanel:
             sizes = [int(v) for v in env.split(",") if v.strip()]
             if sum(sizes) == n and all(v > 0 for v in sizes):
                 return sizes
-        if n <= 1:
-            return [n] if n else []
-        if n <= 3:
-            return [1, n - 1]
-        a = n // 3
-        return [a, a, n - 2 * a]
+        if n <= 0:
+            return []
+        # measured on B200 (profiles/r02h_*): up to 4 GPUs one product over all remote sources wins (0.99 vs 1.05-1.08
+        # ms at 4), at 8 GPUs one product per source (0.67 vs 0.72-0.94 ms)
+        return [n] if self.world_size <= 4 else [1] * n
 
     def build_group_subgraphs(self, sizes: Optional[Sequence[int]] = None):
         """Merge the per-source sub-graphs of consecutive arrivals into one sub-graph per group: its column space is
