@@ -101,13 +101,17 @@ __global__ void slice_bounds_kernel(const TileMeta* __restrict__ tiles, const in
   slice_ptr[static_cast<int64_t>(blockIdx.y) * (grid + 1) + i] = i == grid ? t_hi : (i == 0 ? t_lo : lo);
 }
 
-static int window_cost() {
-  static const int win_cost = [] {
+// Cost of a window in TC blocks for the CTA slices.  Measured (profiles/r02k_window_cost_sweep.txt): plans whose
+// windows are dense enough for the register epilogue (>= 256 TC blocks per window: 16 store instructions per thread
+// and window) want 12 -- reddit-like R-MAT 3.00 -> 2.81 ms -- while the staged epilogue (one bulk copy per window)
+// wants 3: products-like 11.2 ms at 3, 11.9 at 12, 13.4 at 32.  TCGNN_WIN_COST overrides.
+static int window_cost(bool dense_windows) {
+  static const int env = [] {
     const char* e = getenv("TCGNN_WIN_COST");
-    const int v = e ? atoi(e) : 3;
-    return v < 0 ? 0 : (v > 64 ? 64 : v);
+    const int v = e ? atoi(e) : -1;
+    return v > 1024 ? 1024 : v;
   }();
-  return win_cost;
+  return env >= 0 ? env : (dense_windows ? 12 : 3);
 }
 
 __global__ void store_edge_ofs_kernel(TileMeta* tiles, const int32_t* __restrict__ tile_ofs, int32_t num_tiles) {
@@ -244,8 +248,9 @@ int plan_create(const int32_t* row_ptr, const int32_t* col_idx, const int32_t* b
     if (p->num_tiles < p->grid * 8) p->grid = p->num_tiles / 8;
     if (p->grid < 1) p->grid = 1;
     PLAN_CUDA(cudaMalloc(&p->slice_ptr, sizeof(int32_t) * (static_cast<size_t>(p->grid) + 1)));
-    slice_bounds_kernel<<<(p->grid + 256) / 256, 256, 0, stream>>>(p->tiles, p->win_tile_ptr, nullptr, num_windows,
-                                                                   window_cost(), p->grid, p->slice_ptr);
+    slice_bounds_kernel<<<(p->grid + 256) / 256, 256, 0, stream>>>(
+        p->tiles, p->win_tile_ptr, nullptr, num_windows,
+        window_cost(static_cast<int64_t>(p->num_tiles) >= 256LL * num_windows), p->grid, p->slice_ptr);
     count_launch();
     PLAN_CUDA(cudaGetLastError());
     PLAN_CUDA(cudaStreamSynchronize(stream));
@@ -357,7 +362,8 @@ int plan_set_row_chunks(tcgnn_plan* p, const int32_t* win_bounds, int n_chunks, 
     e = cudaMemcpyAsync(d_bounds, win_bounds, sizeof(int32_t) * (n_chunks + 1), cudaMemcpyHostToDevice, stream);
   if (e == cudaSuccess) {
     slice_bounds_kernel<<<dim3((p->grid + 256) / 256, n_chunks), 256, 0, stream>>>(
-        p->tiles, p->win_tile_ptr, d_bounds, p->num_windows, window_cost(), p->grid, table);
+        p->tiles, p->win_tile_ptr, d_bounds, p->num_windows,
+        window_cost(static_cast<int64_t>(p->num_tiles) >= 256LL * p->num_windows), p->grid, table);
     count_launch();
     e = cudaGetLastError();
   }

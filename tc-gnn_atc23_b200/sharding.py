@@ -185,11 +185,10 @@ def calibrated_panel(row_ptr: torch.Tensor, col_idx: torch.Tensor, rank: int, wo
     a_mat = m[:, :2]
     coef, *_ = np.linalg.lstsq(a_mat, m[:, 2], rcond=None)
     a_, b_ = float(coef[0]), float(coef[1])
-    # the overlapped path runs one product per group of sources plus the own one, and each of them walks all windows
-    n_products = 1 if world_size <= 2 else (2 if world_size <= 4 else world_size)
-    if os.environ.get("TCGNN_CALIBRATE_PRODUCTS"):
-        n_products = int(os.environ["TCGNN_CALIBRATE_PRODUCTS"])
-    wc = 3 if a_ <= 0 else int(round(min(max(b_ / a_ * n_products, 0.0), 64.0)))
+    # (scaling the window cost by the number of products of the overlapped step -- each product walks all windows --
+    # was measured and is worse: 0.71 vs 0.605 ms at 8 GPUs, profiles/r02h_*calibrated*)
+    n_products = int(os.environ.get("TCGNN_CALIBRATE_PRODUCTS", "1"))
+    wc = 3 if a_ <= 0 else int(round(min(max(b_ / a_ * n_products, 0.0), 512.0)))
     import TCGNN as _T
     _T.clear_plan_cache()
     del x, xr

@@ -18,4 +18,4 @@ PY
 }
 BARGS="--no-variants --no-e2e" run calib 8 TCGNN_EXCHANGE=auto
 BARGS="--no-variants --no-e2e" run calib_x1 8 TCGNN_EXCHANGE=auto TCGNN_CALIBRATE_PRODUCTS=1
-BARGS="--no-variants --no-e2e" run calib 4 TCGNN_EXCHANGE=auto
+
