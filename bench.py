@@ -436,6 +436,43 @@ class Workload:
         return out
 
 
+class LineGuard:
+    """Keeps the one JSON line safe once the headline is measured: `bail` (an exception in the optional sections) and
+    the deadline timer both emit the result as it stands -- from rank 0; the other ranks just leave -- and end the
+    process with status 0, without waiting for collectives some other rank will never join."""
+
+    def __init__(self, rank, emit, result, deadline_s):
+        import threading
+        self.rank, self.emit, self.result = rank, emit, result
+        self.lock = threading.Lock()
+        self.done = False
+        self.timer = threading.Timer(deadline_s, self.bail, args=(f"deadline of {deadline_s:.0f} s after the headline "
+                                                                  "(TCGNN_BENCH_DEADLINE_S)",))
+        self.timer.daemon = True
+        self.timer.start()
+
+    def bail(self, why):
+        with self.lock:
+            if self.done:
+                return
+            self.done = True
+            log(f"rank {self.rank}: optional sections abandoned: {why}")
+            if self.rank == 0:
+                for _ in range(5):          # the main thread may be adding a key at this very moment
+                    try:
+                        self.emit(dict(self.result, incomplete=why))
+                        break
+                    except RuntimeError:
+                        time.sleep(0.05)
+            sys.stderr.flush()
+            os._exit(0)
+
+    def finish(self):
+        with self.lock:
+            self.done = True
+        self.timer.cancel()
+
+
 def run_variant(name, op, dim, args, world, rank, dev, flush, with_reference):
     """A secondary workload inside the same line: device-timed ms, parity, optionally the reference's kernels."""
     wl = Workload(name, op, dim, args.seed, world, rank, dev)
@@ -604,55 +641,6 @@ def main():
     # ---------------------------------------------------------------- parity of the timed path
     parity = wl.parity()
 
-    # ---------------------------------------------------------------- end to end (host buffers)
-    e2e = None
-    if not args.no_e2e:
-        x_host = wl.x_local.cpu().pin_memory()
-        y_host = torch.empty(tuple(out.shape), dtype=torch.float32).pin_memory()
-        g = wl.graph
-        host_api = world == 1 and os.environ.get("TCGNN_BENCH_E2E", "host") != "torch"
-        api = {"spmm": "TCGNN.forward_host -> tcgnn_spmm_f32_host", "sddmm": "TCGNN.forward_ef_host -> tcgnn_sddmm_f32_host",
-               "agnn": "TCGNN.forward_AGNN_host -> tcgnn_agnn_f32_host"}[args.op] + " (C ABI, host buffers)"
-
-        def e2e_step():
-            if host_api:
-                # the host-buffer entry points: H2D copy, kernels, D2H copy; stream-ordered, so the CUDA events around
-                # the step cover the last copy
-                if args.op == "spmm":
-                    TCGNN.forward_host(x_host, *g, y_host=y_host, sync=False)
-                elif args.op == "sddmm":
-                    TCGNN.forward_ef_host(x_host, *g, edge_out_host=y_host, sync=False)
-                else:
-                    TCGNN.forward_AGNN_host(x_host, g[0], g[1], wl.attention_w, g[2], g[3], g[4], y_host=y_host, sync=False)
-                return
-            xd_buf.copy_(x_host, non_blocking=True)      # a persistent device buffer: the sharded step replays a CUDA graph
-            y_host.copy_(wl.step_from(xd_buf), non_blocking=True)
-
-        xd_buf = torch.empty_like(wl.x_local) if not host_api else None
-        e2e_step()
-        torch.cuda.synchronize()
-        ems, _ = timed_steps(e2e_step, args.steps, 5, flush, world)
-        e2e_ms = float(ems.sum()) / args.steps
-        h2d = x_host.numel() * 4
-        d2h = y_host.numel() * 4
-        if world > 1:
-            tot = torch.tensor([h2d, d2h], dtype=torch.float64, device=dev)
-            dist.all_reduce(tot)
-            h2d, d2h = int(tot[0]), int(tot[1])
-        e2e = {"value": nnz / (e2e_ms * 1e-3), "unit": "edges/s", "ms_per_step": round(e2e_ms, 4),
-               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-               "api": api if host_api else "pinned copy + sharded operator (sharding.RowPanel) + pinned copy",
-               "note": "features from pinned host memory, result back to pinned host memory, every step; the graph "
-                       "(CSR + SGT arrays + plan) stays resident like the reference's main_tcgnn.py:56-60"
-                       + ("; SpMM is pipelined: X arrives in row chunks, every chunk's partial product starts when "
-                          "it has landed, finished output row ranges leave while the next is computed" if host_api and args.op == "spmm" else "")}
-        if host_api and args.op == "spmm":
-            y_chk = TCGNN.forward(wl.x_local, *g)[0]
-            TCGNN.forward_host(x_host, *g, y_host=y_host, sync=True)
-            den = float(y_chk.abs().max())
-            e2e["max_rel_diff_vs_resident"] = float((y_host.to(dev) - y_chk).abs().max()) / max(den, 1e-30)
-            del y_chk
-
     result = {
         "metric": "aggregation edges/s (" + {"spmm": "GCN SpMM", "sddmm": "AGNN SDDMM", "agnn": "AGNN SDDMM + weighted SpMM"}[args.op] + ")",
         "value": value, "unit": "edges/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -661,7 +649,7 @@ def main():
                                        "accumulate in TMEM, fp32 in and out", "data": "synthetic",
         "config": {"workload": wl.string(), "generated": "on device, seeded",
                    "l2": "512 MiB L2 flush before every timed step", "parallelism": wl.exchange_label()},
-        "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "parity": parity, "clocks": clocks,
+        "e2e": None, "gpu_launches": int(launches), "roofline": roofline, "parity": parity, "clocks": clocks,
         "prep": {"graph_gen_s": round(wl.t_graph, 3), "sgt_gpu_s": round(wl.t_sgt, 3), "plan_first_call_s": round(t_plan, 3),
                  "tc_blocks": tiles},
         "min_ms": round(float(ms.min()), 4), "median_ms": round(float(np.median(ms)), 4),
@@ -674,41 +662,98 @@ def main():
             result["exchange"] = dict(st, kernel_ms_on_gathered_matrix=round(k_ms, 4),
                                       note="rank 0's figures; kernel_ms = this rank's panel SpMM on an already gathered matrix")
 
-    # ---------------------------------------------------------------- CPU baseline + secondary workloads
-    if rank == 0 and world == 1 and not args.no_cpu_baseline and args.op == "spmm":
-        try:
-            result["cpu_baseline"] = cpu_spmm_baseline(wl.rp.cpu().numpy(), wl.ci.cpu().numpy(),
-                                                       wl.x_local.cpu().numpy(), dim)
-        except Exception as exc:  # pragma: no cover
-            result["cpu_baseline"] = {"value": None, "unit": "edges/s", "cores": 0, "kind": "port",
-                                      "sample": f"failed: {exc}"}
-    default_line = args.workload == "reddit-like-rmat" and args.op == "spmm" and not args.dim
-    if rank == 0 and world == 1 and default_line and not args.no_cpu_baseline:
-        # BASELINE.json configs[0]: the reference's dgl_baseline GCN run restated on the host cores (timing only)
-        try:
-            sys.path.insert(0, os.path.join(ROOT, "oracle"))
-            import dgl_baseline_cpu
-            result["cpu_baseline_dgl"] = dgl_baseline_cpu.run_best(n_epochs=100)
-        except Exception as exc:  # pragma: no cover
-            result["cpu_baseline_dgl"] = {"failed": repr(exc)}
-    if default_line and not args.no_variants and os.environ.get("TCGNN_BENCH_VARIANTS", "1") != "0":
-        TCGNN.clear_plan_cache()
-        del wl, out
-        torch.cuda.empty_cache()
-        variants = {}
-        names = []
-        if world == 1:
-            names.append(("reddit-like-uniform", True))
-        if world in (1, 8):
-            names.append(("rmat-10m-200m", False))
-        for vname, with_ref in names:
+    # Everything below adds to a headline that is already measured and checked.  A failure or a hang in it (one rank
+    # of eight failing leaves the others inside a collective) must not cost the line: the guard emits what is there
+    # and ends the process with status 0 -- on an exception in any rank, or when the deadline passes.
+    guard = LineGuard(rank, emit, result, float(os.environ.get("TCGNN_BENCH_DEADLINE_S", "360")))
+    try:
+        # ---------------------------------------------------------------- end to end (host buffers)
+        if not args.no_e2e:
+            x_host = wl.x_local.cpu().pin_memory()
+            y_host = torch.empty(tuple(out.shape), dtype=torch.float32).pin_memory()
+            g = wl.graph
+            host_api = world == 1 and os.environ.get("TCGNN_BENCH_E2E", "host") != "torch"
+            api = {"spmm": "TCGNN.forward_host -> tcgnn_spmm_f32_host", "sddmm": "TCGNN.forward_ef_host -> tcgnn_sddmm_f32_host",
+                   "agnn": "TCGNN.forward_AGNN_host -> tcgnn_agnn_f32_host"}[args.op] + " (C ABI, host buffers)"
+
+            def e2e_step():
+                if host_api:
+                    # the host-buffer entry points: H2D copy, kernels, D2H copy; stream-ordered, so the CUDA events around
+                    # the step cover the last copy
+                    if args.op == "spmm":
+                        TCGNN.forward_host(x_host, *g, y_host=y_host, sync=False)
+                    elif args.op == "sddmm":
+                        TCGNN.forward_ef_host(x_host, *g, edge_out_host=y_host, sync=False)
+                    else:
+                        TCGNN.forward_AGNN_host(x_host, g[0], g[1], wl.attention_w, g[2], g[3], g[4], y_host=y_host, sync=False)
+                    return
+                xd_buf.copy_(x_host, non_blocking=True)      # a persistent device buffer: the sharded step replays a CUDA graph
+                y_host.copy_(wl.step_from(xd_buf), non_blocking=True)
+
+            xd_buf = torch.empty_like(wl.x_local) if not host_api else None
+            e2e_step()
+            torch.cuda.synchronize()
+            ems, _ = timed_steps(e2e_step, args.steps, 5, flush, world)
+            e2e_ms = float(ems.sum()) / args.steps
+            h2d = x_host.numel() * 4
+            d2h = y_host.numel() * 4
+            if world > 1:
+                tot = torch.tensor([h2d, d2h], dtype=torch.float64, device=dev)
+                dist.all_reduce(tot)
+                h2d, d2h = int(tot[0]), int(tot[1])
+            e2e = {"value": nnz / (e2e_ms * 1e-3), "unit": "edges/s", "ms_per_step": round(e2e_ms, 4),
+                   "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                   "api": api if host_api else "pinned copy + sharded operator (sharding.RowPanel) + pinned copy",
+                   "note": "features from pinned host memory, result back to pinned host memory, every step; the graph "
+                           "(CSR + SGT arrays + plan) stays resident like the reference's main_tcgnn.py:56-60"
+                           + ("; SpMM is pipelined: X arrives in row chunks, every chunk's partial product starts when "
+                              "it has landed, finished output row ranges leave while the next is computed" if host_api and args.op == "spmm" else "")}
+            if host_api and args.op == "spmm":
+                y_chk = TCGNN.forward(wl.x_local, *g)[0]
+                TCGNN.forward_host(x_host, *g, y_host=y_host, sync=True)
+                den = float(y_chk.abs().max())
+                e2e["max_rel_diff_vs_resident"] = float((y_host.to(dev) - y_chk).abs().max()) / max(den, 1e-30)
+                del y_chk
+            result["e2e"] = e2e
+
+        # ---------------------------------------------------------------- CPU baseline + secondary workloads
+        if rank == 0 and world == 1 and not args.no_cpu_baseline and args.op == "spmm":
             try:
-                variants[vname] = run_variant(vname, "spmm", 0, args, world, rank, dev, flush, with_ref)
-            except Exception as exc:  # pragma: no cover -- a secondary workload never takes the headline down
-                if world > 1:
-                    raise
-                variants[vname] = {"failed": repr(exc)}
-        result["variants"] = variants
+                result["cpu_baseline"] = cpu_spmm_baseline(wl.rp.cpu().numpy(), wl.ci.cpu().numpy(),
+                                                           wl.x_local.cpu().numpy(), dim)
+            except Exception as exc:  # pragma: no cover
+                result["cpu_baseline"] = {"value": None, "unit": "edges/s", "cores": 0, "kind": "port",
+                                          "sample": f"failed: {exc}"}
+        default_line = args.workload == "reddit-like-rmat" and args.op == "spmm" and not args.dim
+        if rank == 0 and world == 1 and default_line and not args.no_cpu_baseline:
+            # BASELINE.json configs[0]: the reference's dgl_baseline GCN run restated on the host cores (timing only)
+            try:
+                sys.path.insert(0, os.path.join(ROOT, "oracle"))
+                import dgl_baseline_cpu
+                result["cpu_baseline_dgl"] = dgl_baseline_cpu.run_best(n_epochs=100)
+            except Exception as exc:  # pragma: no cover
+                result["cpu_baseline_dgl"] = {"failed": repr(exc)}
+        if default_line and not args.no_variants and os.environ.get("TCGNN_BENCH_VARIANTS", "1") != "0":
+            TCGNN.clear_plan_cache()
+            del wl, out
+            torch.cuda.empty_cache()
+            variants = {}
+            names = []
+            if world == 1:
+                names.append(("reddit-like-uniform", True))
+            if world in (1, 8) or os.environ.get("TCGNN_BENCH_VARIANTS") == "all":
+                names.append(("rmat-10m-200m", False))
+            for vname, with_ref in names:
+                try:
+                    variants[vname] = run_variant(vname, "spmm", 0, args, world, rank, dev, flush, with_ref)
+                except Exception as exc:  # pragma: no cover -- a secondary workload never takes the headline down
+                    if world > 1:
+                        raise
+                    variants[vname] = {"failed": repr(exc)}
+            result["variants"] = variants
+    except Exception as exc:  # pragma: no cover
+        guard.bail("after the headline: " + repr(exc))
+    guard.finish()
     if rank == 0:
         emit(result)
     if world > 1:
