@@ -201,7 +201,10 @@ int tcgnn_agnn_f32_host(tcgnn_plan* plan, const float* x_host, int64_t ldx, cons
  * into 1024-byte aligned shared memory, issues `ksteps` tcgen05.mma.kind::tf32 (M=128) whose
  * descriptors are adesc/bdesc (start-address field 0) plus the image base plus k*a_step_bytes /
  * k*b_step_bytes, and returns the 128 x ncols fp32 accumulator (row = TMEM lane) in d_out (HOST
- * memory).  ncols must be 16, 32 or 64 and equal the N of idesc.  Synchronises the stream. */
+ * memory).  ncols must be 16, 32 or 64 and equal the N of idesc.  Synchronises the stream.
+ * adesc == 0: the A operand is taken from TENSOR memory instead -- a_image is then the row-major fp32 matrix
+ * [128][8 * ksteps] (a_bytes = 4096 * ksteps, ksteps <= 24), written with tcgen05.st (lane = row, k-step s in columns
+ * 64 + 8 s ...); a_step_bytes is ignored and idesc must say K-major A. */
 int tcgnn_debug_umma(const void* a_image, int32_t a_bytes, const void* b_image, int32_t b_bytes,
                      uint64_t adesc, uint64_t bdesc, uint32_t idesc, int32_t ksteps, int32_t a_step_bytes,
                      int32_t b_step_bytes, float* d_out, int32_t ncols, void* stream);
@@ -209,7 +212,9 @@ int tcgnn_debug_umma(const void* a_image, int32_t a_bytes, const void* b_image, 
 /* Issue-rate diagnostic (tools/umma_bench.py): `n_mma` back-to-back tcgen05.mma.kind::tf32 from one CTA per
  * grid slot, rotating over n_acc accumulators (acc_stride_cols TMEM columns apart) and n_a / n_b operand
  * tiles in zero-filled shared memory; cycles_out[0] = SM cycles until the last MMA was issued,
- * cycles_out[1] = until the commit after it arrived (block 0).  Synchronises the stream. */
+ * cycles_out[1] = until the commit after it arrived (block 0).  Synchronises the stream.
+ * adesc == 0: A from tensor memory -- groups of 8 MMAs over n_a (<= 56) operand slots of 8 columns, B tiles 512 bytes
+ * apart, one accumulator (n_acc, acc_stride_cols, a_step_bytes, n_b, b_step_bytes ignored). */
 int tcgnn_debug_umma_bench(uint64_t adesc, uint64_t bdesc, uint32_t idesc, int32_t n_mma, int32_t n_acc,
                            int32_t acc_stride_cols, int32_t n_a, int32_t a_step_bytes, int32_t n_b,
                            int32_t b_step_bytes, int32_t grid, int64_t cycles_out[2], void* stream);

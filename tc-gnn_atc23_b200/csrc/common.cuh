@@ -123,8 +123,25 @@ __device__ __forceinline__ void mbar_arrive_after_loads(uint32_t bar, uint32_t d
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+// try_wait suspends the thread until the phase completes or a time limit passes, whichever is first; without a
+// hint the limit is short and a waiting warp comes back to poll (a shared-memory access each time) every ~100
+// cycles.  TCGNN_WAIT_HINT_NS > 0 passes that many nanoseconds as the suspend-time hint.
+#ifndef TCGNN_WAIT_HINT_NS
+#define TCGNN_WAIT_HINT_NS 0
+#endif
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
+#if TCGNN_WAIT_HINT_NS > 0
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity), "r"(static_cast<uint32_t>(TCGNN_WAIT_HINT_NS))
+      : "memory");
+#else
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
@@ -134,6 +151,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "=r"(ok)
       : "r"(bar), "r"(parity)
       : "memory");
+#endif
   return ok != 0;
 }
 // non-blocking test (try_wait may suspend the thread for a while when the phase is not complete)
@@ -181,12 +199,13 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 }
 // Same, for waiters that expect to wait long (epilogue warps): sleep between polls so they do not
 // compete for issue slots and shared-memory bandwidth with the warps on the critical path.
+template <unsigned kSleepNs = 64>
 __device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   uint64_t t0 = 0;
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    __nanosleep(64);
+    __nanosleep(kSleepNs);
     if (TCGNN_WATCHDOG_NS != 0 && (++spins & 0xFFFu) == 0) {
       const uint64_t now = global_timer_ns();
       if (t0 == 0) t0 = now;
@@ -277,6 +296,19 @@ __device__ __forceinline__ uint64_t l2_policy_evict_normal() {
   return p;
 }
 
+// 32-bit read-only global load, raw bits (register gathers of the TS SpMM).  volatile: the loads stay where they are
+// written, i.e. all of a stage's loads are issued before the warp blocks on anything.  -DTCGNN_TS_L1_NOALLOC: do not
+// keep the line in L1.
+__device__ __forceinline__ uint32_t ldg_nc_u32(const char* p) {
+  uint32_t v;
+#ifdef TCGNN_TS_L1_NOALLOC
+  asm volatile("ld.global.nc.L1::no_allocate.b32 %0, [%1];" : "=r"(v) : "l"(p));
+#else
+  asm volatile("ld.global.nc.b32 %0, [%1];" : "=r"(v) : "l"(p));
+#endif
+  return v;
+}
+
 // ---------------------------------------------------------------------------------------------
 // cp.async (SASS: LDGSTS): 16-byte global -> shared copies that bypass registers; completion is
 // reported to an mbarrier, so the issuing warp never waits for the data itself
@@ -291,6 +323,28 @@ __device__ __forceinline__ void cp_async_16_hint(uint32_t smem_dst, const void* 
   asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2, %3;" ::"r"(smem_dst), "l"(gmem_src),
                "r"(src_bytes), "l"(policy)
                : "memory");
+}
+// Feature-row gathers of the SpMM / SDDMM kernels: with or without an L2 evict_last hint (-DTCGNN_X_GATHER_HINT=1).
+// The hint's policy operand costs issue slots on every LDGSTS; whether keeping X in L2 pays for it is a measured,
+// per-kernel choice (profiles/r02m_ldgsts_flavour_ab.txt).
+#ifndef TCGNN_X_GATHER_HINT
+#define TCGNN_X_GATHER_HINT 0
+#endif
+__device__ __forceinline__ uint64_t x_gather_policy() {   // once per warp, outside the loops
+#if TCGNN_X_GATHER_HINT
+  return l2_policy_evict_last();
+#else
+  return 0;
+#endif
+}
+__device__ __forceinline__ void cp_async_16_x(uint32_t smem_dst, const void* gmem_src, uint32_t src_bytes,
+                                              uint64_t policy) {
+#if TCGNN_X_GATHER_HINT
+  cp_async_16_hint(smem_dst, gmem_src, src_bytes, policy);
+#else
+  (void)policy;
+  cp_async_16(smem_dst, gmem_src, src_bytes);
+#endif
 }
 // one arrival on `bar` (counted in its init count: .noinc) once all prior cp.async of this thread landed
 __device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint32_t bar) {
@@ -338,6 +392,26 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Same with the A operand in tensor memory (lane = row m of A, one 32-bit column per k: 128 lanes x 8 columns for
+// M128 K8 tf32; K-major only).  The operand fetch of an MMA then reads shared memory for B alone.
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// registers -> TMEM: thread t of the warp writes 8 consecutive columns of TMEM lane (warp%4)*32+t
+__device__ __forceinline__ void tmem_st_32x32b_x8(uint32_t taddr, const uint32_t (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(v[0]),
+               "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // mbarrier arrives once all previously issued MMAs of this thread have completed
 // (implies tcgen05.fence::before_thread_sync).
 __device__ __forceinline__ void umma_commit(uint32_t bar) {

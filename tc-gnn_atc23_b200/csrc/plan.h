@@ -114,10 +114,11 @@ int agnn_launch(tcgnn_plan* plan, const float* x, int64_t ldx, const float* atte
                 float* att_tile_out, float* edge_out_csr, int32_t dim, uint32_t op_flags, cudaStream_t stream);
 // TCGNN_X_IS_TF32 is honoured only for 16-byte aligned rows of a width that is a multiple of 4: otherwise the last
 // 16-byte vector of a row would pull in whatever follows the first `dim` columns in the caller's matrix (columns
-// that SDDMM would contract over), so the op packs its own zero-padded copy instead.
+// that SDDMM would contract over), so the op packs its own zero-padded copy instead.  The same for a row stride of
+// 2^30 elements or more: the kernels address gathered rows with a 32-bit byte stride.
 inline bool x_is_prerounded(const float* x, int64_t ldx, int32_t dim, uint32_t op_flags) {
   return (op_flags & TCGNN_X_IS_TF32) != 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (ldx & 3) == 0 &&
-         (dim & 3) == 0;
+         (dim & 3) == 0 && ldx < (int64_t{1} << 30);
 }
 int push_rows_launch(const float* src, float* const* peers, int32_t n_peers, const int64_t* seg_begin_rows,
                      const int64_t* seg_end_rows, int32_t n_segs, int64_t ld, cudaStream_t stream);

@@ -56,7 +56,6 @@ constexpr int kSmemBytes = kStages * (kAStageBytes + kBStageBytes) + 2 * kOutSta
 static_assert(kProducers <= kStages, "a warp may not wait for the slot of an own stage it has not published yet");
 static_assert(kMetaStages >= 2 * kProducers, "one feature chunk per group: every in-flight stage is another group");
 static_assert(kSmemBytes <= 232448, "exceeds the 227 KB of dynamic shared memory per CTA");
-constexpr uint32_t kTuneXLast = 16u;                       // gathers with L2 evict_last
 constexpr uint32_t kDbgTrailingCopy = 1u;                  // diagnostics: one more (zero-fill) cp.async closes every stage
 
 template <int kTeam>
@@ -266,9 +265,15 @@ sddmm_tc_kernel(PlanView pv, const int4* __restrict__ groups, int32_t num_groups
     static_assert((kRows * 8 / 32) % kTeam == 0, "the members of a team gather equal shares of a stage");
     const int u_lo = member * kPerLane;
     const int nvec = (dim + 3) >> 2;                  // valid 16-byte vectors per row
-    const uint64_t policy = (flags & kTuneXLast) ? l2_policy_evict_last() : l2_policy_evict_normal();
     const int v = lane & 7;                           // my vector inside the 32-feature chunk
     const int rsub = lane >> 3;                       // my row inside each group of 4 rows
+    const uint64_t policy = x_gather_policy();
+    // row address = one 32 x 32 -> 64 bit multiply-add (row stride < 4 GB: x_is_prerounded); the empty asm keeps
+    // the base in one register pair
+    uint64_t x_bits = reinterpret_cast<uint64_t>(x);
+    asm volatile("" : "+l"(x_bits));
+    const char* x_bytes = reinterpret_cast<const char*>(x_bits);
+    const uint32_t row_bytes = static_cast<uint32_t>(ldx) * 4u;
     int32_t published = pw;                           // oldest own stage not yet published
     int32_t gl = pw / nkc, kc = pw % nkc;
     for (int32_t k = pw; k < n_stages; k += kProducers) {
@@ -315,13 +320,13 @@ sddmm_tc_kernel(PlanView pv, const int4* __restrict__ groups, int32_t num_groups
         const uint32_t dst = (is_a ? a_stage + (row >> 3) * 1024 : b_stage + ((row - 128) >> 3) * 1024) +
                              sw128_offset(row & 7, v);
         const uint32_t sub_step = is_a ? kASubBytes : kBSubBytes;
-        const float* rowp = x + static_cast<int64_t>(node[u] >= 0 ? node[u] : 0) * ldx;
+        const char* rowp = x_bytes + static_cast<uint64_t>(static_cast<uint32_t>(node[u] >= 0 ? node[u] : 0)) * row_bytes;
 #pragma unroll
         for (int sub = 0; sub < 2; ++sub) {
           if (sub == 1 && !second) break;
           const int vg = kc * (kChunk / 4) + sub * 8 + v;    // vector index inside the feature row
           const bool valid = node[u] >= 0 && vg < nvec;
-          cp_async_16_hint(dst + sub * sub_step, rowp + (valid ? vg * 4 : 0), valid ? 16u : 0u, policy);  // zero-fill
+          cp_async_16_x(dst + sub * sub_step, rowp + (valid ? vg * 16 : 0), valid ? 16u : 0u, policy);  // zero-fill
         }
       }
       if (flags & kDbgTrailingCopy) cp_async_16(tmem_slot + 16 + (lane & 1) * 16, x, 0u);
@@ -414,7 +419,7 @@ int sddmm_launch(tcgnn_plan* plan, const float* x, int64_t ldx, float* edge_out_
     }
   }
   const PlanView pv = plan->view();
-  const uint32_t kflags = kTuneXLast | dbg;
+  const uint32_t kflags = dbg;
 #define TCGNN_SDDMM(T)                                                                                      \
   sddmm_tc_kernel<T><<<grid, (kProducerWarp0 + kProducers * T) * 32, kSmemBytes, stream>>>(                \
       pv, plan->groups, plan->num_groups, xr, ldr, raw_tile, tile_out, scale, dim, kflags)

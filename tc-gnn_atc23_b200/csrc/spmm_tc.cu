@@ -65,10 +65,12 @@ constexpr bool kDebugSwitches = false;
 // gathers / the MMAs after a window's first / the B-tile construction / all but one MMA of a full stage
 constexpr uint32_t kAblateGather = 1u, kAblateMma = 2u, kAblateBuild = 4u, kAblateMmaFast = 8u;
 constexpr uint32_t kAblateOutput = 256u;   // no bulk output stores
-// L2 policy switches (env TCGNN_TUNE overrides the default kTuneDefault): feature-row gathers evict_last /
-// tile stream evict_first / output rows written with streaming stores
-constexpr uint32_t kTuneXLast = 16u, kTuneMetaFirst = 32u, kTuneYStream = 64u;
-constexpr uint32_t kTuneDefault = kTuneXLast | kTuneMetaFirst | kTuneYStream;
+// L2 policy switches (env TCGNN_TUNE overrides the default kTuneDefault): tile stream evict_first / output rows
+// written with streaming stores.  The feature-row gathers carry NO cache hint: an evict_last policy operand on every
+// LDGSTS cost 3.5 % (reddit-like R-MAT 2.81 -> 2.72 ms, uniform 4.76 -> 4.59 ms; profiles/r02m_ldgsts_flavour_ab.txt)
+// and the zero-fill size operand nothing.
+constexpr uint32_t kTuneMetaFirst = 32u, kTuneYStream = 64u;
+constexpr uint32_t kTuneDefault = kTuneMetaFirst | kTuneYStream;
 // op mode (not a debug switch): Y += A X -- every window is combined with the bulk reduce-add / fp32 atomics and
 // nothing is cleared first (TCGNN_ACCUMULATE: per-source-panel partial products of the sharded path)
 constexpr uint32_t kFlagAccumulate = 1u << 24;
@@ -80,14 +82,27 @@ constexpr uint32_t kFlagAccumulate = 1u << 24;
 // clock of LDGSTS row gathers however many tiles it keeps in flight (8-10 outstanding 512-byte instructions), so six
 // gathering warps cap an SM at ~38-54 B/clk = 5600-8000 B/clk for the chip, while twelve reach ~10,800 and sixteen
 // ~12,400.  Two warps per stage double the gather issue rate without touching the per-stage barrier protocol.
-template <int DBLK, int G, int S_, int P, int L, bool STAGED, int TEAM = 2>
+// TS: the gathered rows never touch shared memory.  The TEAM = 4 warps of a team sit on the four TMEM lane quadrants;
+// warp q loads features [32q, 32q + 32) of all G x 8 gathered rows of a stage into REGISTERS (coalesced 128-byte
+// loads, 64 in flight per thread), writes them to tensor memory with tcgen05.st (lane = feature, one column per
+// neighbour) and the MMA takes its A operand from there, so no gathered byte crosses shared memory.  Measured
+// (profiles/r02m_spmm_ts_timings.txt, r02m_trace_spmm_ts_*): the layout works (tests/test_gpu_umma_layouts.py), an
+// MMA with A in TMEM costs 55 cycles instead of 39, and the kernel is 1.9x SLOWER than the shared-memory pipeline:
+// a warp-wide 4-byte load moves 128 bytes where an LDGSTS moves 512, every one of the four quadrant warps redoes the
+// address arithmetic of all 64 rows of a stage, and a warp needs ~36 cycles per memory instruction either way
+// (2300 cycles to issue a stage).  Features must lie along the TMEM lanes, so wider loads would need a transpose
+// across warps.  Compiled in profiling builds only (TCGNN_SPMM_TS=1).
+template <int DBLK, int G, int S_, int P, int L, bool STAGED, int TEAM = 2, bool TS = false>
 struct Cfg {
+  static constexpr bool kTs = TS;
   static constexpr int kTeam = TEAM;
   static constexpr int kTilesPerMember = G / TEAM;
   static constexpr bool kStaged = STAGED;
   static constexpr int kG = G;
   static constexpr int kATileBytes = DBLK * 4096;              // DBLK*4 swizzle atoms of 8 rows x 128 B
-  static constexpr int kAStageBytes = kG * kATileBytes;
+  static constexpr int kAStageBytes = TS ? 0 : kG * kATileBytes;
+  static constexpr uint32_t kAccCols = kAcc * DBLK * 16;       // TMEM: accumulator ring (64 / 128 columns) ...
+  static constexpr uint32_t kAStageCols = G * DBLK * 8;        // ... then (TS) the A ring: 8 columns per tile and block
   static constexpr int kBStageBytes = kG * kBTileBytes;
   static constexpr int kMetaStageBytes = kG * static_cast<int>(sizeof(TileMeta));
   static constexpr int kStages = S_;                           // data ring (A + B tiles)
@@ -95,7 +110,7 @@ struct Cfg {
   static constexpr int kOwnLag = L;
   static constexpr int kThreads = (kProducerWarp0 + P * TEAM) * 32;
   static constexpr int kMetaStages = 16;                       // tile-record ring, prefetched far ahead of the data
-  static constexpr uint32_t kTmemCols = kAcc * DBLK * 16;      // 64 / 128
+  static constexpr uint32_t kTmemCols = TS ? 512u : kAccCols;  // a power of two
   static constexpr int kBarBytes = (2 * kMetaStages + 2 * kStages + 2 * kAcc) * 8;
   static constexpr int kYStageBytes = STAGED ? TCGNN_BLK_H * DBLK * 128 * 4 : 0;   // one window of output (8 / 16 KB)
   static constexpr int kSmemBytes = kStages * (kAStageBytes + kBStageBytes) + 2 * kYStageBytes +
@@ -103,6 +118,8 @@ struct Cfg {
                                     1024 /*alignment slack*/;
   static_assert(kG >= 1 && kG <= 8, "the open/close word holds 8 tile bits");
   static_assert(G % TEAM == 0, "the members of a team gather equal shares of a stage");
+  static_assert(!TS || (TEAM == 4 && L == 0 && kAccCols + S_ * kAStageCols <= 512),
+                "TS: one warp per TMEM lane quadrant, eager publication, accumulators + A ring within 512 columns");
   static_assert(kSmemBytes <= 232448, "exceeds the 227 KB of dynamic shared memory per CTA");
   static_assert(kMetaStages >= (L + 1) * P || kMetaStages >= 16, "records of every in-flight own stage stay resident");
   // L == 0: a team publishes the stage it has just filled as soon as its copies have landed (it sits in
@@ -167,6 +184,34 @@ constexpr int kTraceCtas = 160;             // + per-CTA {cycles, tiles, windows
 constexpr int kTraceWords = 3 * kTraceStages * 8 + kTraceCtas * 4 + kTraceStages * 8;   // + epilogue warp 0, per window
 __device__ __forceinline__ void trace_put(long long* trace, int role, int32_t k, int point) {
   if (k < kTraceStages && (threadIdx.x & 31) == 0) trace[(role * kTraceStages + k) * 8 + point] = clock64();
+}
+
+// TS gathers of one tile: element [m][r] = feature block m of gathered row r at this thread's feature, straight into
+// registers.  A tile without padding (all but a window's last) takes the branch-free path: one IMAD.WIDE and one load
+// per element.  Returns the OR of the record's column ids (see mbar_arrive_after_loads).
+template <int DBLK>
+__device__ __forceinline__ uint32_t ts_gather_tile(uint32_t record, const char* const (&base)[DBLK],
+                                                   const uint32_t (&row_bytes)[DBLK], uint32_t (&v)[DBLK][8]) {
+  const int4 c0 = lds_v4(record), c1 = lds_v4(record + 16);   // rows to gather (-1: padding)
+  const int32_t cols[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+  const uint32_t all = static_cast<uint32_t>(c0.x | c0.y | c0.z | c0.w | c1.x | c1.y | c1.z | c1.w);
+  if (static_cast<int32_t>(all) >= 0) {   // warp-uniform
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+      for (int m = 0; m < DBLK; ++m)
+        v[m][r] = ldg_nc_u32(base[m] + static_cast<uint64_t>(static_cast<uint32_t>(cols[r])) * row_bytes[m]);
+  } else {
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+      for (int m = 0; m < DBLK; ++m) {
+        v[m][r] = 0u;
+        if (cols[r] >= 0)
+          v[m][r] = ldg_nc_u32(base[m] + static_cast<uint64_t>(static_cast<uint32_t>(cols[r])) * row_bytes[m]);
+      }
+  }
+  return all;
 }
 
 template <class C, int DBLK>
@@ -299,7 +344,7 @@ spmm_tc_kernel(PlanView pv, const float* __restrict__ x /* tf32-rounded, 16B ali
     // ===================================== MMA issuer ===================================
     // The whole warp runs the loop (warp-uniform control flow keeps addresses and descriptors in uniform
     // registers); one elected lane issues tcgen05.mma / tcgen05.commit.  Per tile: one descriptor add, one MMA.
-    constexpr uint32_t idesc = make_idesc_tf32(128, 16, /*A MN-major*/ true, /*B K-major*/ false);
+    constexpr uint32_t idesc = make_idesc_tf32(128, 16, /*A MN-major (TMEM: K-major)*/ !C::kTs, /*B K-major*/ false);
     // A: MN-major tf32 -> SWIZZLE_128B_BASE32B atoms of 32 features x 4 k-rows (4 x 128 B): feature blocks
     // 1024 B apart (LBO), the two k-halves of a K=8 MMA 512 B apart (SBO)
     const uint64_t adesc0 = make_smem_desc(0, 1024, 512, kSwizzle128BBase32B);
@@ -321,6 +366,7 @@ spmm_tc_kernel(PlanView pv, const float* __restrict__ x /* tf32-rounded, 16B ali
       const int nt = static_cast<int>(info >> 16);
       const uint64_t adesc_s = adesc0 | static_cast<uint64_t>(((a_smem + s * C::kAStageBytes) & 0x3FFFFu) >> 4);
       const uint64_t bdesc_s = bdesc0 | static_cast<uint64_t>(((b_smem + s * C::kBStageBytes) & 0x3FFFFu) >> 4);
+      const uint32_t a_tmem_s = tmem_base + C::kAccCols + s * C::kAStageCols;   // TS: lane 0, first column of the stage
       if (tr) trace_put(trace, 0, k, 1);
       if (info == (static_cast<uint32_t>(kG) << 16) && !skip_mma) {
         // common case in dense windows: a full stage strictly inside one window -> G back-to-back MMAs
@@ -329,9 +375,14 @@ spmm_tc_kernel(PlanView pv, const float* __restrict__ x /* tf32-rounded, 16B ali
           for (int j = 0; j < kG; ++j) {
             if (kDebugSwitches && j > 0 && (flags & kAblateMmaFast)) break;
 #pragma unroll
-            for (int m = 0; m < DBLK; ++m)
-              umma_tf32(acc + m * 16, adesc_s + static_cast<uint64_t>((j * C::kATileBytes + m * 4096) >> 4),
-                        bdesc_s + static_cast<uint64_t>((j * kBTileBytes) >> 4), idesc, 1u);
+            for (int m = 0; m < DBLK; ++m) {
+              if constexpr (C::kTs)
+                umma_tf32_ts(acc + m * 16, a_tmem_s + (j * DBLK + m) * 8,
+                             bdesc_s + static_cast<uint64_t>((j * kBTileBytes) >> 4), idesc, 1u);
+              else
+                umma_tf32(acc + m * 16, adesc_s + static_cast<uint64_t>((j * C::kATileBytes + m * 4096) >> 4),
+                          bdesc_s + static_cast<uint64_t>((j * kBTileBytes) >> 4), idesc, 1u);
+            }
           }
         }
       } else {
@@ -349,9 +400,14 @@ spmm_tc_kernel(PlanView pv, const float* __restrict__ x /* tf32-rounded, 16B ali
             if (elect_one()) {
               if (!skip_mma || first) {
 #pragma unroll
-                for (int m = 0; m < DBLK; ++m)
-                  umma_tf32(acc + m * 16, adesc_s + static_cast<uint64_t>((j * C::kATileBytes + m * 4096) >> 4),
-                            bdesc_s + static_cast<uint64_t>((j * kBTileBytes) >> 4), idesc, first ? 0u : 1u);
+                for (int m = 0; m < DBLK; ++m) {
+                  if constexpr (C::kTs)
+                    umma_tf32_ts(acc + m * 16, a_tmem_s + (j * DBLK + m) * 8,
+                                 bdesc_s + static_cast<uint64_t>((j * kBTileBytes) >> 4), idesc, first ? 0u : 1u);
+                  else
+                    umma_tf32(acc + m * 16, adesc_s + static_cast<uint64_t>((j * C::kATileBytes + m * 4096) >> 4),
+                              bdesc_s + static_cast<uint64_t>((j * kBTileBytes) >> 4), idesc, first ? 0u : 1u);
+                }
               }
               if (last) umma_commit(acc_full + 8 * b);
             }
@@ -395,12 +451,28 @@ spmm_tc_kernel(PlanView pv, const float* __restrict__ x /* tf32-rounded, 16B ali
     constexpr int kVecPerLane = DBLK * 8;     // 8 rows x DBLK*32 vectors / 32 lanes
     const bool skip_gather = kDebugSwitches && (flags & kAblateGather) != 0;
     const bool skip_build = kDebugSwitches && (flags & kAblateBuild) != 0;
-    const uint64_t policy = (flags & kTuneXLast) ? l2_policy_evict_last() : l2_policy_evict_normal();
+    const uint64_t policy = x_gather_policy();
+    // my 16-byte vector of a full-width row; the empty asm keeps the sum in ONE register pair, so a row address is a
+    // single IMAD.WIDE (the compiler otherwise re-adds the kernel parameter after every multiply)
+    uint64_t x_lane_bits = reinterpret_cast<uint64_t>(x) + static_cast<uint64_t>(lane) * 16u;
+    asm volatile("" : "+l"(x_lane_bits));
+    const char* x_lane = reinterpret_cast<const char*>(x_lane_bits);
+    const uint32_t row_bytes = static_cast<uint32_t>(ldx) * 4u;
     // B tile: lane -> 16-byte chunk `lane` of the tile: [n/8][k/4][n%8] x 4 floats (k%4)
     const int bn = (lane >> 4) * 8 + (lane & 7);
     const int bword = bn >> 2;
     const int bshift = (bn & 3) * 8 + ((lane >> 3) & 1) * 4;
     int32_t published = p;                    // oldest own stage not yet published
+    // TS: my feature of block m is m * 128 + 32 * (warp % 4) + lane == my TMEM lane; a lane past `dim` reads x[0]
+    // over and over (stride 0) -- its accumulator rows are never stored
+    const char* ts_base[DBLK];
+    uint32_t ts_row_bytes[DBLK];
+#pragma unroll
+    for (int m = 0; m < DBLK; ++m) {
+      const int f = m * 128 + (warp & 3) * 32 + lane;
+      ts_base[m] = reinterpret_cast<const char*>(x) + (f < dim ? f * 4 : 0);
+      ts_row_bytes[m] = f < dim ? static_cast<uint32_t>(ldx) * 4u : 0u;
+    }
     for (int32_t k = p; k < n_stages; k += kProducers) {
       const int s = k % S;
       const int ms = k % MS;
@@ -481,6 +553,49 @@ spmm_tc_kernel(PlanView pv, const float* __restrict__ x /* tf32-rounded, 16B ali
       }
       const uint32_t fm = __ballot_sync(0xffffffffu, first), lm = __ballot_sync(0xffffffffu, last);
       ring_dep |= fm | lm;
+      if constexpr (C::kTs) {
+        // ---- gather into registers: all loads of the stage are in flight before the slot is even free ----
+        if (trp) trace_put(trace, 1, k / kProducers, 2);
+        uint32_t v[kG][DBLK][8];
+#pragma unroll
+        for (int j = 0; j < kG; ++j) {
+          if (j < nt && !skip_gather) {
+            ring_dep |= ts_gather_tile<DBLK>(meta + j * 64, ts_base, ts_row_bytes, v[j]);
+          } else {
+#pragma unroll
+            for (int m = 0; m < DBLK; ++m)
+#pragma unroll
+              for (int r = 0; r < 8; ++r) v[j][m][r] = 0u;
+          }
+        }
+        if (trp) trace_put(trace, 1, k / kProducers, 3);
+        __syncwarp();
+        if (lane == 0) mbar_arrive_after_loads(meta_empty + 8 * ms, ring_dep);   // the records are in registers
+        if (trp) trace_put(trace, 1, k / kProducers, 4);
+        mbar_wait(empty + 8 * s, ((k / S) & 1) ^ 1u);   // the MMAs of stage k - S have read this A slot and B slot
+        tc_fence_after();
+        if (trp) trace_put(trace, 1, k / kProducers, 5);
+        const uint32_t a_slot = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16) + C::kAccCols + s * C::kAStageCols;
+#pragma unroll
+        for (int j = 0; j < kG; ++j)
+          if (j < nt) {
+#pragma unroll
+            for (int m = 0; m < DBLK; ++m) tmem_st_32x32b_x8(a_slot + (j * DBLK + m) * 8, v[j][m]);
+          }
+        if (trp) trace_put(trace, 1, k / kProducers, 6);
+        if (lane == 0 && member == 0) sts_u32(info_smem + 4 * s, fm | (lm << 8) | (static_cast<uint32_t>(nt) << 16));
+#pragma unroll
+        for (int jj = 0; jj < kTpm; ++jj)
+          if (j_lo + jj < nt) sts_v4(b_smem + s * C::kBStageBytes + (j_lo + jj) * kBTileBytes + lane * 16, bv[jj]);
+        tmem_st_wait();
+        fence_proxy_async_smem();      // B tiles -> the MMA's operand fetch
+        tc_fence_before();             // A columns -> the MMA
+        __syncwarp();
+        if (lane == 0) mbar_arrive(full + 8 * s);
+        published += kProducers;
+        if (trp) trace_put(trace, 1, k / kProducers, 7);
+        continue;
+      }
       // publish the oldest own stage once its copies have landed -- BEFORE blocking on a free slot, so a
       // landed stage never waits for the MMAs of an older one
       if (trp) trace_put(trace, 1, k / kProducers, 2);
@@ -503,18 +618,33 @@ spmm_tc_kernel(PlanView pv, const float* __restrict__ x /* tf32-rounded, 16B ali
             const uint32_t a_tile = a_smem + s * C::kAStageBytes + j * C::kATileBytes;
             const int4 c0 = lds_v4(meta + j * 64), c1 = lds_v4(meta + j * 64 + 16);   // rows to gather (-1: padding)
             const int32_t cols[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
-            ring_dep |= static_cast<uint32_t>(c0.x | c0.y | c0.z | c0.w | c1.x | c1.y | c1.z | c1.w);
-            if (nvec == DBLK * 32) {
+            const uint32_t any = static_cast<uint32_t>(c0.x | c0.y | c0.z | c0.w | c1.x | c1.y | c1.z | c1.w);
+            ring_dep |= any;
+            if (nvec == DBLK * 32 && static_cast<int32_t>(any) >= 0) {
+              // full-width rows, no padding row (every tile of a window but its last): one multiply-add and one
+              // copy per row and 128-feature block, nothing else
+#pragma unroll
+              for (int r = 0; r < 8; ++r) {
+                const char* src = x_lane + static_cast<uint64_t>(static_cast<uint32_t>(cols[r])) * row_bytes;
+#pragma unroll
+                for (int h = 0; h < DBLK; ++h) {
+                  const int v = h * 32 + lane;
+                  cp_async_16_x(a_tile + (v >> 3) * 1024 + sw128_base32_offset(r, v & 7), src + h * 512, 16u, policy);
+                }
+              }
+            } else if (nvec == DBLK * 32) {
               // full-width rows: lane -> vector `lane` (+32) of each of the 8 gathered rows
 #pragma unroll
               for (int r = 0; r < 8; ++r) {
                 const int32_t col = cols[r];
-                const float* src = x + static_cast<int64_t>(col < 0 ? 0 : col) * ldx;
+                // one 32 x 32 -> 64 bit multiply-add per row: my 16 bytes of row `col` (row stride < 4 GB:
+                // x_is_prerounded); the clamp keeps a padding row's unused address inside X
+                const char* src = x_lane + static_cast<uint64_t>(static_cast<uint32_t>(col < 0 ? 0 : col)) * row_bytes;
                 const uint32_t bytes = col < 0 ? 0u : 16u;   // padding column: zero-fill
 #pragma unroll
                 for (int h = 0; h < DBLK; ++h) {
                   const int v = h * 32 + lane;
-                  cp_async_16_hint(a_tile + (v >> 3) * 1024 + sw128_base32_offset(r, v & 7), src + v * 4, bytes, policy);
+                  cp_async_16_x(a_tile + (v >> 3) * 1024 + sw128_base32_offset(r, v & 7), src + h * 512, bytes, policy);
                 }
               }
             } else {
@@ -530,8 +660,7 @@ spmm_tc_kernel(PlanView pv, const float* __restrict__ x /* tf32-rounded, 16B ali
 #pragma unroll
                   for (int i = 1; i < 8; ++i) col = r == i ? cols[i] : col;
                   const float* src = x + static_cast<int64_t>(col < 0 ? 0 : col) * ldx + v * 4;
-                  cp_async_16_hint(a_tile + (v >> 3) * 1024 + sw128_base32_offset(r, v & 7), src, col < 0 ? 0u : 16u,
-                                   policy);
+                  cp_async_16_x(a_tile + (v >> 3) * 1024 + sw128_base32_offset(r, v & 7), src, col < 0 ? 0u : 16u, policy);
                 }
               }
             }
@@ -587,7 +716,7 @@ uint32_t kernel_flags() {
     const char* a = getenv("TCGNN_ABLATE");
     const char* t = getenv("TCGNN_TUNE");
     const uint32_t ablate = a ? static_cast<uint32_t>(strtoul(a, nullptr, 0)) & 0x30Fu : 0u;
-    const uint32_t tune = t ? static_cast<uint32_t>(strtoul(t, nullptr, 0)) & (kTuneXLast | kTuneMetaFirst | kTuneYStream)
+    const uint32_t tune = t ? static_cast<uint32_t>(strtoul(t, nullptr, 0)) & (kTuneMetaFirst | kTuneYStream)
                             : kTuneDefault;
     const char* c = getenv("TCGNN_TRACE_CTA");
     const uint32_t cta = c ? (static_cast<uint32_t>(atoi(c)) & 0xFFu) << 16 : 0u;   // bits [16,24)
@@ -702,6 +831,26 @@ cudaError_t launch_pass(const tcgnn_plan* plan, const PlanView& pv, int grid, co
     if (preset == 1) return lag == 1 ? TCGNN_LAUNCH_TL(T / 2, 12, 12, false, 1, 1) : TCGNN_LAUNCH_TL(T / 2, 12, 12, false, 1, 0);
     return lag == 1 ? TCGNN_LAUNCH_TL(T / 2, 10, 10, true, 1, 1) : TCGNN_LAUNCH_TL(T / 2, 10, 10, true, 1, 0);
   }
+#ifdef TCGNN_DEBUG_SWITCHES
+  // Register gathers + A operand in tensor memory (Cfg::kTs), profiling builds only: TCGNN_SPMM_TS=1 selects it,
+  // TCGNN_SPMM_TS_GROUPS the number of gathering teams (3: 18 warps, 4: 22 warps).  Correct (tests/test_gpu_spmm.py
+  // passes with it) and 1.9x SLOWER than the shared-memory pipeline -- kept as the measured alternative.
+  static const int ts_env = [] {
+    const char* e = getenv("TCGNN_SPMM_TS");
+    return e != nullptr ? atoi(e) : 0;
+  }();
+  static const int ts_groups = [] {
+    const char* e = getenv("TCGNN_SPMM_TS_GROUPS");
+    return e != nullptr ? atoi(e) : 3;
+  }();
+  if (ts_env != 0) {
+#define TCGNN_LAUNCH_TS(STAGED, NG) \
+  launch_kernel<Cfg<DBLK, T, 6, NG, 0, STAGED, 4, true>, DBLK>(plan, pv, grid, xr, ldr, wperm, y, ldy, dim, mode_flags, stream)
+    if (preset == 1) return ts_groups == 4 ? TCGNN_LAUNCH_TS(false, 4) : TCGNN_LAUNCH_TS(false, 3);
+    return ts_groups == 4 ? TCGNN_LAUNCH_TS(true, 4) : TCGNN_LAUNCH_TS(true, 3);
+#undef TCGNN_LAUNCH_TS
+  }
+#endif
   switch (preset) {
     case 1: TCGNN_LAUNCH(T, 6, 6, false);
 #ifdef TCGNN_DEBUG_SWITCHES

@@ -12,6 +12,7 @@ namespace {
 
 constexpr int kProbeMaxA = 96 * 1024;
 constexpr int kProbeMaxB = 32 * 1024;
+constexpr uint32_t kProbeTmemCols = 256;   // accumulator in [0, 64), A operand (adesc == 0) from column 64
 
 __global__ void __launch_bounds__(128, 1)
 umma_probe_kernel(const uint8_t* __restrict__ a_img, int a_bytes, const uint8_t* __restrict__ b_img, int b_bytes,
@@ -33,19 +34,34 @@ umma_probe_kernel(const uint8_t* __restrict__ a_img, int a_bytes, const uint8_t*
     mbar_init(&done_bar, 1);
     fence_mbar_init();
   }
-  if (warp == 0) tmem_alloc<64>(&tmem_slot);
+  if (warp == 0) tmem_alloc<kProbeTmemCols>(&tmem_slot);
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
+  const bool a_in_tmem = adesc == 0;   // the A image is then row-major [128][8 * ksteps] fp32
+  if (a_in_tmem) {
+    // thread (warp, lane) owns TMEM lane 32 * warp + lane = row m of A; k-step s sits in columns 64 + 8 s ...
+    const float* arow = reinterpret_cast<const float*>(a_smem) + (warp * 32 + lane) * 8 * ksteps;
+    for (int k = 0; k < ksteps; ++k) {
+      uint32_t v[8];
+      for (int i = 0; i < 8; ++i) v[i] = __float_as_uint(arow[k * 8 + i]);
+      tmem_st_32x32b_x8(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + 64 + k * 8, v);
+    }
+    tmem_st_wait();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+  }
 
   if (threadIdx.x == 0) {
     const uint32_t a_addr = smem_u32(a_smem), b_addr = smem_u32(b_smem);
     for (int k = 0; k < ksteps; ++k) {
       const uint64_t ad = adesc + static_cast<uint64_t>(((a_addr + k * a_step) & 0x3FFFFu) >> 4);
       const uint64_t bd = bdesc + static_cast<uint64_t>(((b_addr + k * b_step) & 0x3FFFFu) >> 4);
-      umma_tf32(tmem_base, ad, bd, idesc, k > 0 ? 1u : 0u);
+      if (a_in_tmem) umma_tf32_ts(tmem_base, tmem_base + 64 + k * 8, bd, idesc, k > 0 ? 1u : 0u);
+      else umma_tf32(tmem_base, ad, bd, idesc, k > 0 ? 1u : 0u);
     }
     umma_commit(&done_bar);
   }
@@ -61,7 +77,7 @@ umma_probe_kernel(const uint8_t* __restrict__ a_img, int a_bytes, const uint8_t*
   __syncthreads();
   if (warp == 0) {
     tc_fence_after();
-    tmem_dealloc<64>(tmem_base);
+    tmem_dealloc<kProbeTmemCols>(tmem_base);
   }
 }
 
@@ -94,7 +110,19 @@ umma_bench_kernel(uint64_t adesc, uint64_t bdesc, uint32_t idesc, int n_mma, int
     const uint64_t ad0 = adesc + static_cast<uint64_t>((a_addr & 0x3FFFFu) >> 4);
     const uint64_t bd0 = bdesc + static_cast<uint64_t>((b_addr & 0x3FFFFu) >> 4);
     const long long t0 = clock64();
-    if (n_acc == 0) {
+    if (adesc == 0) {
+      // A from tensor memory: groups of 8 MMAs over n_a operand slots of 8 columns (from column 64), B tiles 512 B apart
+      int ia = 0;
+      for (int i = 0; i < n_mma; i += 8) {
+        if (elect_one()) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            umma_tf32_ts(tmem_base, tmem_base + 64 + ((ia + j) % n_a) * 8, bd0 + static_cast<uint64_t>((j * 512) >> 4),
+                         idesc, 1u);
+        }
+        ia = (ia + 8) % n_a;
+      }
+    } else if (n_acc == 0) {
       // production pattern: groups of 8 MMAs with compile-time operand offsets (4 KB A tiles, 512 B B tiles)
       for (int i = 0; i < n_mma; i += 8) {
         if (elect_one()) {
@@ -138,7 +166,8 @@ int debug_umma_bench(uint64_t adesc, uint64_t bdesc, uint32_t idesc, int32_t n_m
                      int32_t n_a, int32_t a_step, int32_t n_b, int32_t b_step, int32_t grid, int64_t* cycles_out,
                      cudaStream_t stream) {
   if (cycles_out == nullptr || n_mma < 1 || n_acc < 0 || n_a < 1 || n_b < 1 || grid < 1 ||
-      static_cast<int64_t>(n_acc) * acc_stride > 512 || static_cast<int64_t>(n_a) * a_step > kProbeMaxA ||
+      static_cast<int64_t>(n_acc) * acc_stride > 512 ||
+      (adesc != 0 ? static_cast<int64_t>(n_a) * a_step > kProbeMaxA : n_a > 56) ||
       static_cast<int64_t>(n_b) * b_step > kProbeMaxB) {
     set_last_error("tcgnn_debug_umma_bench: bad argument");
     return TCGNN_ERR_INVALID_ARG;
@@ -172,6 +201,7 @@ int debug_umma(const void* a_image, int32_t a_bytes, const void* b_image, int32_
                float* d_out, int32_t ncols, cudaStream_t stream) {
   if (a_image == nullptr || b_image == nullptr || d_out == nullptr || a_bytes <= 0 || b_bytes <= 0 ||
       a_bytes % 16 != 0 || b_bytes % 16 != 0 || a_bytes > kProbeMaxA || b_bytes > kProbeMaxB || ksteps < 1 ||
+      (adesc == 0 && (a_bytes != 128 * 8 * 4 * ksteps || ksteps > 24)) ||
       (ncols != 16 && ncols != 32 && ncols != 64)) {
     set_last_error("tcgnn_debug_umma: bad argument");
     return TCGNN_ERR_INVALID_ARG;

@@ -172,3 +172,22 @@ def test_tf32_operand_handling_is_exact_after_rna(capi):
     trunc = (raw.view(np.uint32) & np.uint32(0xFFFFE000)).view(np.float32)
     mode = "truncate" if np.array_equal(got[:, :8], trunc) else ("rna" if np.array_equal(got[:, :8], orc.tf32_rna(raw)) else "other")
     _report(f"raw fp32 operand handling by kind::tf32 = {mode}", True, 0.0)
+
+
+@pytest.mark.parametrize("ksteps", [1, 3])
+def test_a_operand_from_tensor_memory(capi, ksteps):
+    """The register-gather SpMM: A (gathered rows, lane = feature, one column per neighbour k) written to TMEM with
+    tcgen05.st.32x32b.x8 and consumed from there (K-major), B = the 16x8 tile from shared memory as before."""
+    rng = np.random.default_rng(3 + ksteps)
+    A = rng.integers(-8, 9, size=(128, 8 * ksteps)).astype(np.float32)
+    Bs = rng.integers(-4, 5, size=(ksteps, 16, 8)).astype(np.float32)
+    want = sum(A[:, 8 * s:8 * s + 8] @ Bs[s].T for s in range(ksteps))
+    b_img = np.concatenate([image_b_kmajor_noswizzle(Bs[s], 128, 256) for s in range(ksteps)])
+    got = capi.debug_umma(np.ascontiguousarray(A), b_img, 0, smem_desc(128, 256, SW_NONE),
+                          idesc_tf32(128, 16, False, False), ksteps, 0, 512)
+    err = float(np.abs(got - want).max())
+    _report(f"A from TMEM (tcgen05.st x8, K-major), ksteps={ksteps}", err == 0.0, err)
+    if err != 0.0:
+        np.save(f"gpurun_out/umma_probe_ts_got_{ksteps}.npy", got)
+        np.save(f"gpurun_out/umma_probe_ts_want_{ksteps}.npy", want)
+    assert err == 0.0

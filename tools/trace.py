@@ -14,9 +14,18 @@ names = {
     1: ["top", "meta ready", "B values+flags", "prev landed", "prev published", "slot free", "gathers issued", "B stored"],
     2: ["top", "slot free", "TMA issued"],
 }
+import os
+if os.environ.get("TCGNN_SPMM_TS", "0") != "0":   # register-gather pipeline: different points
+    names[1] = ["top", "meta ready", "B values+flags", "loads issued", "records released", "slot free", "tcgen05.st issued", "published"]
 for role, label in ((0, "MMA warp (per stage)"), (1, "producer warp 0 (per own stage)"), (2, "meta loader (per stage)")):
     r = t[role, lo:hi]
     n = len(names[role])
+    if role == 1:
+        r = t[role, 10:85]                      # own stages only: far fewer samples per CTA
+        keep = (r > 0).all(axis=0)             # points this pipeline shape never records (lag 0: "prev landed")
+        r = r[:, keep]
+        names[1] = [nm for nm, k in zip(names[1], keep) if k]
+        n = len(names[1])
     ok = (r[:, :n] > 0).all(axis=1)
     r = r[ok]
     if len(r) < 2:

@@ -31,6 +31,17 @@ def run(name, adesc, bdesc, idesc, n_mma, n_acc, acc_stride, n_a, a_step, n_b, b
     print(f"{name:70s} n={n_mma:5d} issue {out[0] / n_mma:7.1f} cyc/MMA   complete {out[1] / n_mma:7.1f} cyc/MMA", flush=True)
 
 
+if len(sys.argv) > 1 and sys.argv[1] == "ts":
+    # A operand from tensor memory (adesc == 0): the operand fetch reads shared memory for the 512-byte B tile only
+    b_k = smem_desc(128, 256, SW_NONE)
+    a_mn = smem_desc(1024, 512, SW_128B_BASE32B)
+    for grid in (1, 148):
+        run(f"A in smem   M128 N16 K8 x8 grid {grid}", a_mn, b_k, idesc_tf32(128, 16, True, False), 2048, 0, 16, 8, 4096, 8, 512, grid=grid)
+        run(f"A in TMEM   M128 N16 K8 x8 grid {grid}", 0, b_k, idesc_tf32(128, 16, False, False), 2048, 0, 16, 48, 0, 8, 512, grid=grid)
+    run("A in TMEM   M128 N32 K8 x8", 0, b_k, idesc_tf32(128, 32, False, False), 2048, 0, 32, 48, 0, 8, 512)
+    run("A in TMEM   M128 N64 K8 x8", 0, b_k, idesc_tf32(128, 64, False, False), 2048, 0, 64, 48, 0, 8, 512)
+    sys.exit(0)
+
 k128 = smem_desc(16, 1024, SW_128B)               # SDDMM: K-major 128B swizzle
 a_mn = smem_desc(1024, 512, SW_128B_BASE32B)      # SpMM A: MN-major, 4 KB per K=8 tile
 b_k = smem_desc(128, 256, SW_NONE)                # SpMM B: K-major 16x8
