@@ -296,9 +296,10 @@ sddmm_tc_kernel(PlanView pv, const int4* __restrict__ groups, int32_t num_groups
         }
       }
       // the ring slot may be refilled as soon as this arrive lands: every row id must be IN its register first
-      uint32_t dep = static_cast<uint32_t>(ntiles ^ win);
+      uint32_t node_or = 0u;
 #pragma unroll
-      for (int u = 0; u < kPerLane; ++u) dep |= static_cast<uint32_t>(node[u]);
+      for (int u = 0; u < kPerLane; ++u) node_or |= static_cast<uint32_t>(node[u]);
+      const uint32_t dep = node_or | static_cast<uint32_t>(ntiles ^ win);
       __syncwarp();
       if (lane == 0) mbar_arrive_after_loads(meta_empty + 8 * ms, dep);
       // publish the previous own stage once its copies have landed -- BEFORE blocking on a free slot
@@ -313,6 +314,22 @@ sddmm_tc_kernel(PlanView pv, const int4* __restrict__ groups, int32_t num_groups
       const uint32_t a_stage = a_smem + s * kAStageBytes;
       const uint32_t b_stage = b_smem + s * kBStageBytes;
       const bool second = dim - kc * kChunk > 32;            // the MMAs read the second sub-block too
+      // every row of the stage exists and the chunk holds all 64 features (all stages of a full group at D % 64 == 0):
+      // one multiply-add and two copies per row, no clamps, no zero-fill predicates
+      const bool plain = __all_sync(0xffffffffu, static_cast<int32_t>(node_or) >= 0) && dim - kc * kChunk >= kChunk;
+      if (plain) {
+#pragma unroll
+        for (int u = 0; u < kPerLane; ++u) {
+          const int row = (u_lo + u) * 4 + rsub;
+          const bool is_a = row < 128;
+          const uint32_t dst = (is_a ? a_stage + (row >> 3) * 1024 : b_stage + ((row - 128) >> 3) * 1024) +
+                               sw128_offset(row & 7, v);
+          const char* rowp = x_bytes + static_cast<uint64_t>(static_cast<uint32_t>(node[u])) * row_bytes +
+                             (kc * (kChunk / 4) + v) * 16;
+          cp_async_16_x(dst, rowp, 16u, policy);
+          cp_async_16_x(dst + (is_a ? kASubBytes : kBSubBytes), rowp + 128, 16u, policy);
+        }
+      } else
 #pragma unroll
       for (int u = 0; u < kPerLane; ++u) {
         const int row = (u_lo + u) * 4 + rsub;

@@ -487,7 +487,8 @@ spmm_tc_kernel(PlanView pv, const float* __restrict__ x /* tf32-rounded, 16B ali
       float4 bv[kTpm];
       uint32_t ring_dep = 0u;   // every word read from the record ring, see mbar_arrive_after_loads
       if (wperm == nullptr) {
-        // pattern: my four cells are four bits of one mask word
+        // pattern: my four cells are four bits of one mask word (expanding them through a 16-entry float4 table in
+        // shared memory instead of the selects was 2 % slower: profiles/r02o_timings_final.txt)
 #pragma unroll
         for (int jj = 0; jj < kTpm; ++jj) {
           const int j = j_lo + jj;
