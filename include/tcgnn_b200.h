@@ -120,8 +120,8 @@ int tcgnn_sddmm_f32(tcgnn_plan* plan, const float* x, int64_t ldx, float* edge_o
  * use, TCGNN_kernel.cu:436-444); tcgnn_spmm_f32 / tcgnn_sddmm_f32 make that copy on every call.  A caller that
  * feeds the same X to several ops (AGNN: SDDMM + weighted SpMM) or that ships X between GPUs (row-panel
  * sharding: round the local panel once, all-gather the rounded rows) rounds once with tcgnn_round_tf32 and passes
- * TCGNN_X_IS_TF32 to the *_ex entry points.  The flag is honoured when x is 16-byte aligned and ldx % 4 == 0
- * (otherwise the op packs a copy as usual).  out: [rows, ldo] with ldo % 4 == 0, 16-byte aligned; columns
+ * TCGNN_X_IS_TF32 to the *_ex entry points.  The flag is honoured when x is 16-byte aligned, ldx % 4 == 0,
+ * dim % 4 == 0 and ldx < 2^30 (otherwise the op packs a copy as usual).  out: [rows, ldo] with ldo % 4 == 0, 16-byte aligned; columns
  * [dim, ldo) are zero-filled. */
 #define TCGNN_X_IS_TF32 1u
 /* SpMM only: Y += A X instead of Y = A X (nothing is cleared; every window is combined with fp32 reduce-adds).  Used
