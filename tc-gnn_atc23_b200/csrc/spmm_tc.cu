@@ -25,8 +25,8 @@
 //   warp  5     meta loader  TMA bulk copies (UBLKCP, L2 evict_first) of the tile records into a 16-deep
 //                            ring that runs far ahead of the data stages
 //   warps 6-11  producers    warp p OWNS the stages k = p (mod 6): it gathers all G tiles of the stage with
-//                            asynchronous 128-bit copies (cp.async / LDGSTS, zero-fill for padding, L2
-//                            evict_last) straight into the swizzled (128B rows, 32B granule) MN-major A
+//                            asynchronous 128-bit copies (cp.async / LDGSTS, zero-fill for padding, no
+//                            cache hint) straight into the swizzled (128B rows, 32B granule) MN-major A
 //                            tiles, expands the occupancy masks (or edge weights) into the K-major B tiles,
 //                            writes the stage's open/close word, and publishes the stage with ONE mbarrier
 //                            arrive once cp.async.wait_group says its copies have landed.
